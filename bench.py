@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract for the spblas B200 backend.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload c2|c1|c4|c3k32|c3k128]
+
+Workload at N=1 (the configuration BASELINE.json's metric is quoted on, configs[1]):
+  C2 — 2D Poisson 5-point stencil on a 4096 x 4096 grid, CSR SpMV in fp64 with int32
+  indices/offsets, iterated y -> x with scaled(1/8, A).  A "step" is one
+  product x <- (1/8) A x over the whole matrix (1.34 GB of operands, larger than L2, so
+  consecutive steps cannot be served from cache; no flush needed).
+At N>1 the run is WEAK-scaled: every rank owns one 4096 x 4096 grid's worth of rows of the
+(4096 N) x 4096 grid, x is replicated, and the y -> x step exchanges only the halo the
+inspect phase found necessary (spblas_reference_b200/sharded.py).  value = GFLOP/s over all
+ranks, time = max over ranks (CUDA events).
+
+`--impl reference` times the reference's own CPU multiply on the host (oracle/_ref when it
+was built from /root/reference, else the oracle port) on the same workload.
+
+Everything measured goes through the public host API -> C ABI -> sm_100a kernels.  The
+oracle is used only for cpu_baseline / --impl reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2",
+                    choices=["c1", "c2", "c3k32", "c3k128", "c4"])
+    ap.add_argument("--grid", type=int, default=4096, help="C2 grid edge (per GPU)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------
+# algorithmic (compulsory) work, SURVEY §8d
+# ----------------------------------------------------------------------------------------
+def spmv_bytes(nnz, m, n_touched, sT, sI, sO):
+    return nnz * (sT + sI) + (m + 1) * sO + n_touched * sT + m * sT
+
+
+def spmm_bytes(nnz, m, n, k, sT, sI, sO):
+    return nnz * (sT + sI) + (m + 1) * sO + n * k * sT + m * k * sT
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smmax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smmax),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU multiply on the host
+# ----------------------------------------------------------------------------------------
+def host_matrix_c2(g, gi, r0, r1):
+    import torch
+    from spblas_reference_b200 import generators as G
+    v, rp, ci, shape = G.poisson2d_csr(g, torch.float64, "cpu", r0, r1, gi=gi)
+    return v.numpy(), rp.numpy(), ci.numpy(), shape
+
+
+def cpu_reference_spmv_seconds(v, rp, ci, shape, x, reps, alpha):
+    """Times y = alpha A x with the reference's CPU multiply (1 thread: the reference is
+    serial).  Returns (best seconds, kind)."""
+    from oracle import oracle as O
+    O.build()
+    impl, kind = ("reference", "reference") if O.have_ref() else ("oracle", "port")
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.spmv("csr", shape, rp, ci, v, x, alpha_a=alpha, impl=impl)
+        best = min(best, time.perf_counter() - t0)
+    return best, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    g = args.grid
+    v, rp, ci, shape = host_matrix_c2(g, g, 0, g * g)
+    m, n = shape
+    nnz = len(ci)
+    x = np.ones(n, dtype=np.float64)
+    from oracle import oracle as O
+    O.build()
+    impl, kind = ("reference", "reference") if O.have_ref() else ("oracle", "port")
+    for _ in range(max(1, min(args.warmup, 3))):
+        y = O.spmv("csr", shape, rp, ci, v, x, alpha_a=0.125, impl=impl)
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        y = O.spmv("csr", shape, rp, ci, v, x, alpha_a=0.125, impl=impl)
+        x = y
+    dt = (time.perf_counter() - t0) / steps
+    gflops = 2.0 * nnz / dt / 1e9
+    line = {
+        "impl": "reference", "metric": "CSR SpMV GFLOP/s", "value": gflops, "unit": "GFLOP/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"C2 poisson2d {g}x{g} CSR SpMV fp64/int32, iterated y->x, "
+                               "alpha=1/8 via scaled(); one full product per step",
+                   "rows": m, "nnz": nnz},
+        "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": 1, "kind": kind,
+                         "sample": "the full product, every step (reference CPU multiply is "
+                                   "serial: 1 thread)",
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gbs": spmv_bytes(nnz, m, n, 8, 4, 4) / dt / 1e9,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import spblas_reference_b200 as sb
+    from spblas_reference_b200 import generators as G
+    from spblas_reference_b200.sharded import ShardedSpMV, equal_row_blocks
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 backend has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    K, W = max(1, args.steps), max(3, args.warmup)
+    peak, peak_src = measured_peak()
+
+    if args.workload != "c2":
+        from bench_extra import run_extra   # single-GPU side workloads (C1, C3, C4)
+        run_extra(args, sb, G, dev, peak, peak_src, ClockSampler(local_rank))
+        return
+
+    # ---- C2: one g x g grid of rows per rank --------------------------------------------
+    g = args.grid
+    gi = g * world
+    n = gi * g
+    blocks = equal_row_blocks(n, world)
+    r0, r1 = blocks[rank]
+    v, rp, ci, shape = G.poisson2d_csr(g, torch.float64, dev, r0, r1, gi=gi)
+    m_loc, nnz_loc = shape[0], int(ci.numel())
+    a = sb.csr_view(v, rp, ci, shape, nnz_loc)
+    a_scaled = sb.scaled(0.125, a)
+    cmin, cmax = int(ci.min()), int(ci.max())
+
+    x0 = torch.ones(n, dtype=torch.float64, device=dev)
+    info = sb.multiply_inspect(a, x0, torch.empty(m_loc, dtype=torch.float64, device=dev))
+    t_ins0 = time.perf_counter()
+    sb.multiply_inspect(info, a, x0, torch.empty(m_loc, dtype=torch.float64, device=dev))
+    torch.cuda.synchronize()
+    inspect_ms = (time.perf_counter() - t_ins0) * 1e3
+
+    op = ShardedSpMV(n, blocks, (cmin, cmax + 1),
+                     lambda x, y: sb.multiply_execute(info, a_scaled, x, y),
+                     torch.float64, dev)
+    op.set_x(x0)
+    del x0
+
+    # ---- warm-up, then the timed region ---------------------------------------------------
+    for _ in range(W):
+        op.step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = info.total_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        op.step()
+    e1.record()
+    barrier()
+    step_ms = max_over_ranks(e0.elapsed_time(e1) / K)
+    launches = int(sum_over_ranks(info.total_launches - launches0))
+
+    # kernel-only loop (no exchange) for the roofline of the dominant kernel
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    k0.record()
+    for _ in range(K):
+        op.multiply()
+    k1.record()
+    barrier()
+    kern_ms = max_over_ranks(k0.elapsed_time(k1) / K)
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_nnz = int(sum_over_ranks(nnz_loc))
+    flops_step = 2.0 * total_nnz
+    value = flops_step / (step_ms * 1e-3) / 1e9
+    x_touched = min(n, cmax - cmin + 1)
+    bytes_launch = spmv_bytes(nnz_loc, m_loc, x_touched, 8, 4, 4)
+    achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
+
+    # ---- end to end through the public API with HOST buffers --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        x_host = torch.ones(n, dtype=torch.float64).pin_memory()
+        y_host = torch.empty(m_loc, dtype=torch.float64).pin_memory()
+        x_dev = torch.empty(n, dtype=torch.float64, device=dev)
+        y_dev = torch.empty(m_loc, dtype=torch.float64, device=dev)
+        ke = max(3, min(K, 10))
+
+        def e2e_step():
+            x_dev.copy_(x_host, non_blocking=True)          # H2D of the step's input
+            sb.multiply_execute(info, a_scaled, x_dev, y_dev)
+            y_host.copy_(y_dev, non_blocking=True)          # D2H of the step's result
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            e2e_step()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) / ke * 1e3)
+        e2e = {"value": flops_step / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
+               "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(m_loc * 8),
+               "ms_per_step": e2e_ms, "steps": ke,
+               "what": "pinned host x -> device, multiply_execute, y -> pinned host; A and "
+                       "the inspected plan stay resident (operator reuse, as in the y->x loop)"}
+        # sanity: the result is the known answer A*1/8 (interior rows 0)
+        assert torch.isfinite(y_host).all()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        vh, rph, cih = v.cpu().numpy(), rp.cpu().numpy(), ci.cpu().numpy()
+        xh = np.ones(n, dtype=np.float64)
+        reps = 5
+        sec, kind = cpu_reference_spmv_seconds(vh, rph, cih, shape, xh, reps, 0.125)
+        cpu = {"value": 2.0 * nnz_loc / sec / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": kind,
+               "sample": f"the full {g}x{g} product, best of {reps} (reference CPU multiply is "
+                         "serial: 1 thread)",
+               "seconds": sec, "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": "CSR SpMV GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"C2 poisson2d {g}x{g} per GPU ({gi}x{g} global) CSR SpMV fp64/int32, "
+                            "iterated y->x, alpha=1/8 via scaled(); one full product per step",
+                "rows_per_gpu": m_loc, "nnz_per_gpu": nnz_loc, "parallelism": f"rowblock{world}",
+                "exchange": op.plan.mode, "halo_elems_per_step": op.plan.recv_elems,
+                "l2_policy": "inputs larger than L2 (1.34 GB per product), no flush",
+                "inspect_ms": inspect_ms,
+            },
+            "gbs": bytes_launch * world / (step_ms * 1e-3) / 1e9,
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic("c2"),
+                "kernel": "spmv_merge_tile_kernel<double,int,int> (+ carry fix-up, ~1% of the step)",
+                "algorithmic_bytes_per_launch": bytes_launch, "kernel_ms": kern_ms,
+                "peak_source": peak_src,
+                "frac_of_nominal_8TBs": achieved / 8000.0,
+            },
+            "clocks": clocks,
+            "gpu_launches": launches,
+            "e2e": e2e,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

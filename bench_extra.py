@@ -1,0 +1,113 @@
+"""Side workloads for bench.py (--workload c1|c3k32|c3k128|c4): the other BASELINE.json
+configs on ONE GPU.  They are parity-test cases, not the headline bench line; this prints
+the same JSON shape so that profiles/ can hold their roofline numbers too.
+
+C1 is 92 MB — it fits in the 126 MB L2 — so its timed loop rotates over enough independent
+copies of the operands to exceed 2x L2 (cold-L2 protocol)."""
+import json
+import time
+
+import torch
+
+
+def _bytes_spmv(nnz, m, n, sT, sI=4, sO=4):
+    return nnz * (sT + sI) + (m + 1) * sO + n * sT + m * sT
+
+
+def _bytes_spmm(nnz, m, n, k, sT, sI=4, sO=4):
+    return nnz * (sT + sI) + (m + 1) * sO + n * k * sT + m * k * sT
+
+
+def _time_loop(fn, steps, warmup):
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_extra(args, sb, G, dev, peak, peak_src, sampler):
+    K, W = max(1, args.steps), max(3, args.warmup)
+    wl = args.workload
+    extra = {}
+    if wl == "c1":
+        m = n = 1_000_000
+        copies = 4                                    # 4 x 92 MB > 2 x L2
+        mats = []
+        for c in range(copies):
+            v, rp, ci, shape = G.uniform_random_csr(m, n, 10, seed=c, dtype=torch.float32, device=dev)
+            a = sb.csr_view(v, rp, ci, shape, int(ci.numel()))
+            x = torch.ones(n, device=dev)
+            y = torch.empty(m, device=dev)
+            mats.append((a, x, y, sb.multiply_inspect(a, x, y)))
+        nnz = mats[0][0].nnz
+
+        def fn(i):
+            a, x, y, info = mats[i % copies]
+            sb.multiply_execute(info, sb.scaled(1.2, a), x, y)
+        flops, nbytes, dtype = 2.0 * nnz, _bytes_spmv(nnz, m, n, 4), "f32"
+        name = "C1 uniform random CSR SpMV fp32/int32 m=n=1M, 10 nnz/row, scaled(1.2, a)"
+        extra["l2_policy"] = f"rotating over {copies} independent operand sets (cold L2)"
+        launches_of = lambda: sum(t[3].total_launches for t in mats)
+    elif wl == "c4":
+        v, rp, ci, shape = G.rmat_csr(24, 16, seed=24, dtype=torch.float32, device=dev)
+        m, n = shape
+        nnz = int(ci.numel())
+        a = sb.csr_view(v, rp, ci, shape, nnz)
+        x = G.dense_uniform((n,), 5, torch.float32, dev)
+        y = torch.empty(m, device=dev)
+        t0 = time.perf_counter()
+        info = sb.multiply_inspect(a, x, y)
+        torch.cuda.synchronize()
+        extra["inspect_ms"] = (time.perf_counter() - t0) * 1e3
+        extra["max_row_len"] = info.max_row_len
+        extra["empty_rows"] = info.empty_rows
+
+        def fn(i):
+            sb.multiply_execute(info, a, x, y)
+        flops, nbytes, dtype = 2.0 * nnz, _bytes_spmv(nnz, m, n, 4), "f32"
+        name = "C4 R-MAT scale 24 (edge factor 16) CSR SpMV fp32/int32"
+        extra["l2_policy"] = "inputs larger than L2 (2.3 GB)"
+        launches_of = lambda: info.total_launches
+    else:
+        k = 32 if wl == "c3k32" else 128
+        m = n = 2_000_000
+        v, rp, ci, shape = G.uniform_random_csr(m, n, 16, seed=3, dtype=torch.float32, device=dev)
+        nnz = int(ci.numel())
+        a = sb.csr_view(v, rp, ci, shape, nnz)
+        B = G.dense_uniform((n, k), 4, torch.float32, dev)
+        C = torch.empty((m, k), device=dev)
+        info = sb.multiply_inspect(a, B, C)
+
+        def fn(i):
+            sb.multiply_execute(info, a, B, C)
+        flops, nbytes, dtype = 2.0 * nnz * k, _bytes_spmm(nnz, m, n, k, 4), "f32"
+        name = f"C3 CSR SpMM fp32 2M x 2M, 16 nnz/row, row-major B k={k}"
+        extra["l2_policy"] = "inputs larger than L2"
+        extra["gather_model_bytes"] = nnz * 8 + (m + 1) * 4 + nnz * k * 4 + m * k * 4
+        launches_of = lambda: info.total_launches
+
+    sampler.start()
+    l0 = launches_of()
+    ms = _time_loop(fn, K, W)
+    launches = launches_of() - l0
+    clocks = sampler.stop()
+    achieved = nbytes / (ms * 1e-3) / 1e9
+    line = {
+        "metric": "CSR SpMM GFLOP/s" if wl.startswith("c3") else "CSR SpMV GFLOP/s",
+        "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": 1, "steps": K,
+        "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": dict(workload=name, nnz=nnz, **extra),
+        "gbs": achieved,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src},
+        "clocks": clocks, "gpu_launches": int(launches - W * (launches // (K + W)) if False else launches),
+    }
+    print(json.dumps(line), flush=True)

@@ -1,0 +1,198 @@
+/*
+ * spblas_b200.h — C ABI of the B200 (sm_100a) backend for the sparse-times-dense
+ * hot path of SparseBLAS/spblas-reference.
+ *
+ * This is the drop-in boundary: the C++ backend headers under
+ * include/spblas/vendor/b200/ (selected with -DSPBLAS_ENABLE_B200, i.e. CMake
+ * -DENABLE_B200=ON) decode the reference's views and call ONLY the functions
+ * declared here.  Everything behind this header is hand-written CUDA compiled
+ * for sm_100a (libspblas_b200.so); there is no cuSPARSE, no CPU fallback.
+ *
+ * All pointers named `d_*` are DEVICE pointers (the same contract the
+ * reference's GPU backends have: test/gtest/device/spmv_test.cpp:27-34 puts
+ * raw device pointers in csr_view / std::span).  Scalars (`alpha`) are HOST
+ * pointers to one element of the value type.
+ *
+ * Every entry point returns an int status (0 = success) and never throws.
+ * The C++ headers turn statuses into the reference's exception types
+ * (include/spblas/vendor/cusparse/exception.hpp:13-21,
+ *  include/spblas/algorithms/multiply_impl.hpp:37-41,70-75).
+ *
+ * Reference interface each entry point replaces:
+ *   spblas_b200_plan_create/destroy   <- __cusparse::operation_state_t / spmv_state_t
+ *                                        (vendor/cusparse/operation_state_t.hpp:10-37,
+ *                                         vendor/cusparse/detail/spmv_state_t.hpp:11-52)
+ *   spblas_b200_inspect               <- multiply_inspect (algorithms/multiply.hpp:9-13,29-33;
+ *                                        no-op in algorithms/multiply_impl.hpp:19-29,105-116;
+ *                                        real work only in vendor/onemkl_sycl/spmv_impl.hpp:34-60)
+ *   spblas_b200_spmv                  <- multiply(info, a, x, y) SpMV
+ *                                        (algorithms/multiply_impl.hpp:33-62,
+ *                                         vendor/cusparse/spmv_impl.hpp:19-90)
+ *   spblas_b200_spmm                  <- multiply(info, a, B, C) SpMM
+ *                                        (algorithms/multiply_impl.hpp:66-101,
+ *                                         vendor/onemkl_sycl/spmm_impl.hpp:88-125)
+ *   spblas_b200_plan_query            <- (new) exposes the inspect-phase metadata so the
+ *                                        structure tests can compare it bit-exactly
+ */
+#ifndef SPBLAS_B200_H
+#define SPBLAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SPBLAS_B200_API
+#else
+#define SPBLAS_B200_API __attribute__((visibility("default")))
+#endif
+
+#define SPBLAS_B200_VERSION 100
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+  SPBLAS_B200_SUCCESS = 0,
+  SPBLAS_B200_INVALID_ARGUMENT = 1, /* bad enum / null pointer / negative size      */
+  SPBLAS_B200_SHAPE_MISMATCH = 2,   /* -> std::invalid_argument in the C++ header   */
+  SPBLAS_B200_NOT_SUPPORTED = 3,    /* type combination not instantiated            */
+  SPBLAS_B200_ALLOC_FAILED = 4,     /* -> std::bad_alloc                            */
+  SPBLAS_B200_CUDA_ERROR = 5,       /* -> std::runtime_error("CUDA encountered ..") */
+  SPBLAS_B200_NOT_INSPECTED = 6,    /* execute called on a plan with no structure   */
+  SPBLAS_B200_INVALID_STRUCTURE = 7 /* rowptr not monotone / offsets out of range   */
+};
+
+/* ---- enums -------------------------------------------------------------- */
+enum { SPBLAS_B200_CSR = 0, SPBLAS_B200_CSC = 1 };
+/* index / offset element types (csr_view<T, I, O>: views/csr_view.hpp:12) */
+enum { SPBLAS_B200_I32 = 0, SPBLAS_B200_I64 = 1 };
+/* value types (vendor/cusparse/types.hpp:17-20 allows fp + int32; complex is rejected) */
+enum { SPBLAS_B200_F32 = 0, SPBLAS_B200_F64 = 1, SPBLAS_B200_S32 = 2 };
+
+/* inspect flags */
+enum {
+  SPBLAS_B200_INSPECT_DEFAULT = 0,
+  /* Skip the row-length histogram (partition table only).  Used by the
+     no-`info` multiply(a, x, y) overload, which re-derives the partition on
+     every call because it may not assume the structure is unchanged. */
+  SPBLAS_B200_INSPECT_LIGHT = 1
+};
+
+/* plan_query selectors.  All integer outputs are int64_t. */
+enum {
+  SPBLAS_B200_Q_NUM_TILES = 0,      /* int64[1]: merge-path tiles of the SpMV partition        */
+  SPBLAS_B200_Q_TILE_ITEMS = 1,     /* int64[1]: merge items (row ends + nonzeros) per tile    */
+  SPBLAS_B200_Q_TILE_STARTS = 2,    /* int64[2*(num_tiles+1)]: (row, nnz) start of every tile  */
+  SPBLAS_B200_Q_ROWLEN_HIST = 3,    /* int64[SPBLAS_B200_HIST_BINS]: log2 row-length histogram */
+  SPBLAS_B200_Q_MAX_ROW_LEN = 4,    /* int64[1]                                                */
+  SPBLAS_B200_Q_EMPTY_ROWS = 5,     /* int64[1]                                                */
+  SPBLAS_B200_Q_SPMV_VARIANT = 6,   /* int64[1]: kernel variant chosen for SpMV */
+  SPBLAS_B200_Q_LAST_LAUNCHES = 7,  /* int64[1]: kernels launched by the last execute call     */
+  SPBLAS_B200_Q_TOTAL_LAUNCHES = 8, /* int64[1]: kernels launched through this plan so far     */
+  SPBLAS_B200_Q_CSR_ROWPTR = 9,     /* offset_t[rows+1]: effective CSR rowptr (CSC: transpose) */
+  SPBLAS_B200_Q_CSR_COLIND = 10,    /* index_t[nnz]:    effective CSR colind                   */
+  SPBLAS_B200_Q_CSR_PERM = 11,      /* offset_t[nnz]:   value gather permutation (CSC only)    */
+  SPBLAS_B200_Q_NUM_SEGMENTS = 12,  /* int64[1]: SpMM row segments (0 = rows are not split)    */
+  SPBLAS_B200_Q_SEGMENTS = 13,      /* int64[3*num_segments]: (row, nnz_begin, nnz_end)        */
+  SPBLAS_B200_Q_SPMM_VARIANT = 14   /* int64[1]: kernel variant of the last SpMM               */
+};
+
+/* Row-length histogram: bin 0 = empty rows, bin b >= 1 = rows with
+   2^(b-1) <= len < 2^b.  (Row length = rowptr[i+1]-rowptr[i], the definition the
+   reference's row() uses: backend/view_customizations.hpp:52-53.) */
+#define SPBLAS_B200_HIST_BINS 40
+
+typedef struct spblas_b200_plan spblas_b200_plan;
+
+/* ---- plan lifetime ------------------------------------------------------ */
+
+/* Create an empty plan bound to `cuda_stream` (a cudaStream_t; NULL = legacy
+   default stream, which is what the reference's GPU tests rely on:
+   test/gtest/device/spmv_test.cpp:34-36 calls multiply then copies back). */
+SPBLAS_B200_API int spblas_b200_plan_create(spblas_b200_plan** plan,
+                                            void* cuda_stream);
+SPBLAS_B200_API void spblas_b200_plan_destroy(spblas_b200_plan* plan);
+SPBLAS_B200_API int spblas_b200_plan_set_stream(spblas_b200_plan* plan,
+                                                void* cuda_stream);
+
+/* ---- inspect ------------------------------------------------------------ */
+
+/* Analyse the structure of A (m x n, nnz stored entries) on the GPU:
+     - validates the offsets array (monotone; ptr[0] may be any base >= 0, as a
+       row-block shard of a larger matrix has; ptr[last]-ptr[0] must equal nnz),
+     - row-length histogram, max row length, empty-row count,
+     - merge-path partition table over (row ends + nonzeros),
+     - CSC: builds the row-major (CSR) image of A by a stable counting sort:
+       rowptr/colind of the transpose-of-the-storage plus a value permutation,
+     - SpMM (k_hint > 1): row segments for rows longer than the segment limit.
+   format   SPBLAS_B200_CSR: d_ptr = rowptr[m+1], d_ind = colind[nnz]
+            SPBLAS_B200_CSC: d_ptr = colptr[n+1], d_ind = rowind[nnz]
+   The plan keeps d_ptr/d_ind (not owned); they must stay alive and structurally
+   unchanged until the plan is destroyed or re-inspected.  Values may change
+   freely between executes. */
+SPBLAS_B200_API int spblas_b200_inspect(spblas_b200_plan* plan, int format,
+                                        int64_t m, int64_t n, int64_t nnz,
+                                        const void* d_ptr, const void* d_ind,
+                                        int off_type, int idx_type,
+                                        int64_t k_hint, int flags);
+
+/* ---- execute ------------------------------------------------------------ */
+
+/* y[m] = alpha * A * x[n]   (beta = 0: y is overwritten, stale contents —
+   including NaN — are discarded, as multiply_impl.hpp:43-46 zeroes y first).
+   Uses the inspected structure.  Enqueued on the plan's stream; no host
+   synchronisation, no allocation. */
+SPBLAS_B200_API int spblas_b200_spmv(spblas_b200_plan* plan, int val_type,
+                                     const void* alpha, const void* d_values,
+                                     const void* d_x, void* d_y);
+
+/* C[m x k] = alpha * A * B[n x k], B and C row-major with leading dimensions
+   ldb, ldc (>= k) in elements. */
+SPBLAS_B200_API int spblas_b200_spmm(spblas_b200_plan* plan, int val_type,
+                                     const void* alpha, const void* d_values,
+                                     const void* d_B, int64_t ldb, void* d_C,
+                                     int64_t ldc, int64_t k);
+
+/* One-shot forms used by the overloads that take no operation_info_t
+   (vendor/cusparse/spmv_impl.hpp:92-102 creates and destroys a cuSPARSE handle
+   per call there).  They run a LIGHT inspect on a thread-local cached plan
+   (buffers are reused, never assumed valid) and then execute. */
+SPBLAS_B200_API int spblas_b200_spmv_once(
+    void* cuda_stream, int format, int64_t m, int64_t n, int64_t nnz,
+    const void* d_ptr, const void* d_ind, int off_type, int idx_type,
+    int val_type, const void* alpha, const void* d_values, const void* d_x,
+    void* d_y);
+SPBLAS_B200_API int spblas_b200_spmm_once(
+    void* cuda_stream, int format, int64_t m, int64_t n, int64_t nnz,
+    const void* d_ptr, const void* d_ind, int off_type, int idx_type,
+    int val_type, const void* alpha, const void* d_values, const void* d_B,
+    int64_t ldb, void* d_C, int64_t ldc, int64_t k);
+
+/* ---- introspection / errors ---------------------------------------------- */
+
+/* Copies the selected metadata into `out` (HOST memory, `bytes` capacity).
+   Synchronises the plan's stream.  Returns INVALID_ARGUMENT when `bytes` is too
+   small; *needed (optional) receives the required size. */
+SPBLAS_B200_API int spblas_b200_plan_query(spblas_b200_plan* plan, int what,
+                                           void* out, size_t bytes,
+                                           size_t* needed);
+
+/* Message of the last failure on this plan ("" if none).  Owned by the plan. */
+SPBLAS_B200_API const char* spblas_b200_last_error(const spblas_b200_plan* plan);
+/* Message of the last failure of a *_once call on this thread. */
+SPBLAS_B200_API const char* spblas_b200_last_error_once(void);
+SPBLAS_B200_API const char* spblas_b200_status_string(int status);
+SPBLAS_B200_API int spblas_b200_version(void);
+
+/* Debug/tuning knob (also read from the environment variable
+   SPBLAS_B200_SPMV_VARIANT at plan creation): force a SpMV kernel variant for
+   ncu A/B runs.  -1 = automatic. */
+SPBLAS_B200_API int spblas_b200_plan_force_variant(spblas_b200_plan* plan,
+                                                   int spmv_variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPBLAS_B200_H */

@@ -1,0 +1,404 @@
+// cabi.cu — the extern "C" surface declared in include/spblas_b200.h.
+// Argument validation, plan lifetime, error strings and metadata queries.  No
+// compute here; kernels live in inspect.cu / spmv.cu / spmm.cu.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "plan.hpp"
+
+namespace b200 {
+
+int fail(spblas_b200_plan* p, int status, const std::string& msg) {
+  if (p)
+    p->err = msg;
+  return status;
+}
+
+int cuda_fail(spblas_b200_plan* p, cudaError_t e, const char* what) {
+  std::string msg = "CUDA encountered an error ";
+  msg += cudaGetErrorName(e);
+  msg += ": \"";
+  msg += cudaGetErrorString(e);
+  msg += "\" in ";
+  msg += what;
+  if (p)
+    p->err = msg;
+  return e == cudaErrorMemoryAllocation ? SPBLAS_B200_ALLOC_FAILED
+                                        : SPBLAS_B200_CUDA_ERROR;
+}
+
+void release(DeviceBuffer& b) {
+  if (b.p)
+    cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+int reserve(spblas_b200_plan* p, DeviceBuffer& b, size_t bytes) {
+  if (bytes == 0)
+    bytes = 16;
+  if (b.cap >= bytes)
+    return SPBLAS_B200_SUCCESS;
+  release(b);
+  // grow geometrically so that the cached one-shot plan settles quickly
+  size_t want = bytes + bytes / 4;
+  want = (want + 255) & ~size_t(255);
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    (void)cudaGetLastError();
+    return fail(p, SPBLAS_B200_ALLOC_FAILED, "device allocation failed");
+  }
+  b.cap = want;
+  return SPBLAS_B200_SUCCESS;
+}
+
+namespace {
+
+void release_all(spblas_b200_plan* p) {
+  DeviceBuffer* bufs[] = {&p->own_rowptr,  &p->own_colind, &p->own_perm,
+                          &p->sort_tmp0,   &p->sort_tmp1,  &p->sort_tmp2,
+                          &p->sort_ws,     &p->tile_starts, &p->carry_row,
+                          &p->carry_val,   &p->segments,   &p->seg_partial,
+                          &p->seg_counter, &p->stats};
+  for (DeviceBuffer* b : bufs)
+    release(*b);
+}
+
+bool valid_index_type(int t) { return t == SPBLAS_B200_I32 || t == SPBLAS_B200_I64; }
+bool valid_value_type(int t) {
+  return t == SPBLAS_B200_F32 || t == SPBLAS_B200_F64 || t == SPBLAS_B200_S32;
+}
+
+thread_local std::string g_once_error;
+struct OncePlanHolder {
+  spblas_b200_plan* plan = nullptr;
+  ~OncePlanHolder() {
+    // The CUDA context may already be gone at thread/process exit; leak the
+    // device buffers rather than call into a dead runtime.
+    plan = nullptr;
+  }
+};
+thread_local OncePlanHolder g_once;
+
+} // namespace
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int spblas_b200_version(void) { return SPBLAS_B200_VERSION; }
+
+const char* spblas_b200_status_string(int status) {
+  switch (status) {
+  case SPBLAS_B200_SUCCESS:
+    return "success";
+  case SPBLAS_B200_INVALID_ARGUMENT:
+    return "invalid argument";
+  case SPBLAS_B200_SHAPE_MISMATCH:
+    return "shape mismatch";
+  case SPBLAS_B200_NOT_SUPPORTED:
+    return "not supported";
+  case SPBLAS_B200_ALLOC_FAILED:
+    return "allocation failed";
+  case SPBLAS_B200_CUDA_ERROR:
+    return "CUDA error";
+  case SPBLAS_B200_NOT_INSPECTED:
+    return "plan holds no inspected structure";
+  case SPBLAS_B200_INVALID_STRUCTURE:
+    return "invalid sparse structure";
+  default:
+    return "unknown status";
+  }
+}
+
+int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
+  if (!out)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  *out = nullptr;
+  spblas_b200_plan* p = new (std::nothrow) spblas_b200_plan();
+  if (!p)
+    return SPBLAS_B200_ALLOC_FAILED;
+  p->stream = static_cast<cudaStream_t>(cuda_stream);
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e != cudaSuccess) {
+    delete p;
+    return SPBLAS_B200_CUDA_ERROR;
+  }
+  int sms = 0;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+  if (e != cudaSuccess) {
+    delete p;
+    return SPBLAS_B200_CUDA_ERROR;
+  }
+  p->num_sms = sms > 0 ? sms : 148;
+  if (const char* v = std::getenv("SPBLAS_B200_SPMV_VARIANT"))
+    p->forced_variant = std::atoi(v);
+  *out = p;
+  return SPBLAS_B200_SUCCESS;
+}
+
+void spblas_b200_plan_destroy(spblas_b200_plan* p) {
+  if (!p)
+    return;
+  release_all(p);
+  delete p;
+}
+
+int spblas_b200_plan_set_stream(spblas_b200_plan* p, void* cuda_stream) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->stream = static_cast<cudaStream_t>(cuda_stream);
+  return SPBLAS_B200_SUCCESS;
+}
+
+int spblas_b200_plan_force_variant(spblas_b200_plan* p, int v) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->forced_variant = v;
+  return SPBLAS_B200_SUCCESS;
+}
+
+int spblas_b200_inspect(spblas_b200_plan* p, int format, int64_t m, int64_t n,
+                        int64_t nnz, const void* d_ptr, const void* d_ind,
+                        int off_type, int idx_type, int64_t k_hint, int flags) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  p->inspected = false;
+  if (format != SPBLAS_B200_CSR && format != SPBLAS_B200_CSC)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "format must be CSR or CSC");
+  if (!valid_index_type(off_type) || !valid_index_type(idx_type))
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "index/offset type must be int32 or int64");
+  if (m < 0 || n < 0 || nnz < 0)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "negative dimension");
+  const int64_t majors = format == SPBLAS_B200_CSR ? m : n;
+  if (majors > 0 && d_ptr == nullptr)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "offsets pointer is null");
+  if (nnz > 0 && d_ind == nullptr)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "indices pointer is null");
+  if (majors == 0 && nnz != 0)
+    return fail(p, SPBLAS_B200_INVALID_STRUCTURE, "nnz != 0 with no rows/columns");
+  const int64_t imax = idx_type == SPBLAS_B200_I32 ? 0x7fffffff : INT64_MAX;
+  if (m > imax || n > imax)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "dimension exceeds index type");
+  if (off_type == SPBLAS_B200_I32 && nnz > 0x7fffffff)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "nnz exceeds offset type");
+
+  p->format = format;
+  p->m = m;
+  p->n = n;
+  p->nnz = nnz;
+  p->user_ptr = d_ptr;
+  p->user_ind = d_ind;
+  p->off_type = off_type;
+  p->idx_type = idx_type;
+  p->k_hint = k_hint < 1 ? 1 : k_hint;
+
+  int rc = inspect_structure(p, flags);
+  if (rc == SPBLAS_B200_SUCCESS)
+    p->inspected = true;
+  return rc;
+}
+
+int spblas_b200_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
+                     const void* d_values, const void* d_x, void* d_y) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  if (!p->inspected)
+    return fail(p, SPBLAS_B200_NOT_INSPECTED, "spmv called before inspect");
+  if (!valid_value_type(val_type))
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "value type must be f32, f64 or s32");
+  if (!alpha)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "alpha is null");
+  if ((p->nnz > 0 && !d_values) || (p->n > 0 && p->nnz > 0 && !d_x) ||
+      (p->m > 0 && !d_y))
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null device pointer");
+  return run_spmv(p, val_type, alpha, d_values, d_x, d_y);
+}
+
+int spblas_b200_spmm(spblas_b200_plan* p, int val_type, const void* alpha,
+                     const void* d_values, const void* d_B, int64_t ldb,
+                     void* d_C, int64_t ldc, int64_t k) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  if (!p->inspected)
+    return fail(p, SPBLAS_B200_NOT_INSPECTED, "spmm called before inspect");
+  if (!valid_value_type(val_type))
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "value type must be f32, f64 or s32");
+  if (!alpha)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "alpha is null");
+  if (k < 0)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "negative k");
+  if (ldb < k || ldc < k)
+    return fail(p, SPBLAS_B200_SHAPE_MISMATCH, "leading dimension smaller than k");
+  if (k > 0 && ((p->nnz > 0 && (!d_values || !d_B)) || (p->m > 0 && !d_C)))
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null device pointer");
+  return run_spmm(p, val_type, alpha, d_values, d_B, ldb, d_C, ldc, k);
+}
+
+static int once_plan(void* stream, spblas_b200_plan** out) {
+  if (!g_once.plan) {
+    int rc = spblas_b200_plan_create(&g_once.plan, stream);
+    if (rc) {
+      g_once_error = "could not create the one-shot plan";
+      return rc;
+    }
+  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev != g_once.plan->device) {
+    // buffers belong to another device: start over on this one
+    spblas_b200_plan_destroy(g_once.plan);
+    g_once.plan = nullptr;
+    int rc = spblas_b200_plan_create(&g_once.plan, stream);
+    if (rc) {
+      g_once_error = "could not create the one-shot plan";
+      return rc;
+    }
+  }
+  g_once.plan->stream = static_cast<cudaStream_t>(stream);
+  *out = g_once.plan;
+  return SPBLAS_B200_SUCCESS;
+}
+
+int spblas_b200_spmv_once(void* stream, int format, int64_t m, int64_t n,
+                          int64_t nnz, const void* d_ptr, const void* d_ind,
+                          int off_type, int idx_type, int val_type,
+                          const void* alpha, const void* d_values,
+                          const void* d_x, void* d_y) {
+  g_once_error.clear();
+  spblas_b200_plan* p = nullptr;
+  int rc = once_plan(stream, &p);
+  if (rc)
+    return rc;
+  rc = spblas_b200_inspect(p, format, m, n, nnz, d_ptr, d_ind, off_type, idx_type,
+                           1, SPBLAS_B200_INSPECT_LIGHT);
+  if (rc == SPBLAS_B200_SUCCESS)
+    rc = spblas_b200_spmv(p, val_type, alpha, d_values, d_x, d_y);
+  if (rc)
+    g_once_error = p->err;
+  // the one-shot plan must not outlive the caller's structure pointers
+  p->inspected = false;
+  return rc;
+}
+
+int spblas_b200_spmm_once(void* stream, int format, int64_t m, int64_t n,
+                          int64_t nnz, const void* d_ptr, const void* d_ind,
+                          int off_type, int idx_type, int val_type,
+                          const void* alpha, const void* d_values,
+                          const void* d_B, int64_t ldb, void* d_C, int64_t ldc,
+                          int64_t k) {
+  g_once_error.clear();
+  spblas_b200_plan* p = nullptr;
+  int rc = once_plan(stream, &p);
+  if (rc)
+    return rc;
+  // SpMM wants to know about very long rows, so this is a full inspect.
+  rc = spblas_b200_inspect(p, format, m, n, nnz, d_ptr, d_ind, off_type, idx_type,
+                           k, SPBLAS_B200_INSPECT_DEFAULT);
+  if (rc == SPBLAS_B200_SUCCESS)
+    rc = spblas_b200_spmm(p, val_type, alpha, d_values, d_B, ldb, d_C, ldc, k);
+  if (rc)
+    g_once_error = p->err;
+  p->inspected = false;
+  return rc;
+}
+
+const char* spblas_b200_last_error(const spblas_b200_plan* p) {
+  return p ? p->err.c_str() : "";
+}
+
+const char* spblas_b200_last_error_once(void) { return g_once_error.c_str(); }
+
+int spblas_b200_plan_query(spblas_b200_plan* p, int what, void* out,
+                           size_t bytes, size_t* needed) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  auto scalar = [&](int64_t v) -> int {
+    if (needed)
+      *needed = sizeof(int64_t);
+    if (!out || bytes < sizeof(int64_t))
+      return out ? fail(p, SPBLAS_B200_INVALID_ARGUMENT, "query buffer too small")
+                 : SPBLAS_B200_SUCCESS;
+    std::memcpy(out, &v, sizeof(v));
+    return SPBLAS_B200_SUCCESS;
+  };
+  auto device_array = [&](const void* d, size_t n) -> int {
+    if (needed)
+      *needed = n;
+    if (!out)
+      return SPBLAS_B200_SUCCESS;
+    if (bytes < n)
+      return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "query buffer too small");
+    if (n == 0)
+      return SPBLAS_B200_SUCCESS;
+    B200_CUDA_TRY(p, cudaMemcpyAsync(out, d, n, cudaMemcpyDeviceToHost, p->stream));
+    B200_CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    return SPBLAS_B200_SUCCESS;
+  };
+  switch (what) {
+  case SPBLAS_B200_Q_LAST_LAUNCHES:
+    return scalar(p->last_launches);
+  case SPBLAS_B200_Q_TOTAL_LAUNCHES:
+    return scalar(p->total_launches);
+  default:
+    break;
+  }
+  if (!p->inspected)
+    return fail(p, SPBLAS_B200_NOT_INSPECTED, "query on a plan with no structure");
+  const size_t so = type_size_idx(p->off_type), si = type_size_idx(p->idx_type);
+  switch (what) {
+  case SPBLAS_B200_Q_NUM_TILES:
+    return scalar(p->num_tiles);
+  case SPBLAS_B200_Q_TILE_ITEMS:
+    return scalar(p->tile_items);
+  case SPBLAS_B200_Q_TILE_STARTS:
+    return device_array(p->tile_starts.p,
+                        size_t(p->num_tiles + 1) * 2 * sizeof(int64_t));
+  case SPBLAS_B200_Q_ROWLEN_HIST: {
+    const size_t n = sizeof(int64_t) * SPBLAS_B200_HIST_BINS;
+    if (needed)
+      *needed = n;
+    if (!out)
+      return SPBLAS_B200_SUCCESS;
+    if (bytes < n)
+      return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "query buffer too small");
+    if (!p->have_hist)
+      return fail(p, SPBLAS_B200_NOT_INSPECTED, "histogram was skipped (light inspect)");
+    std::memcpy(out, p->hist, n);
+    return SPBLAS_B200_SUCCESS;
+  }
+  case SPBLAS_B200_Q_MAX_ROW_LEN:
+    return scalar(p->max_row_len);
+  case SPBLAS_B200_Q_EMPTY_ROWS:
+    return scalar(p->empty_rows);
+  case SPBLAS_B200_Q_SPMV_VARIANT:
+    return scalar(p->spmv_variant);
+  case SPBLAS_B200_Q_SPMM_VARIANT:
+    return scalar(p->spmm_variant);
+  case SPBLAS_B200_Q_CSR_ROWPTR:
+    return device_array(p->csr_rowptr, size_t(p->csr_rows + 1) * so);
+  case SPBLAS_B200_Q_CSR_COLIND:
+    return device_array(static_cast<const char*>(p->csr_colind) +
+                            (p->csr_perm ? 0 : size_t(p->base) * si),
+                        size_t(p->nnz) * si);
+  case SPBLAS_B200_Q_CSR_PERM:
+    if (!p->csr_perm)
+      return device_array(nullptr, 0);
+    return device_array(p->csr_perm, size_t(p->nnz) * so);
+  case SPBLAS_B200_Q_NUM_SEGMENTS:
+    return scalar(p->num_segments);
+  case SPBLAS_B200_Q_SEGMENTS:
+    return device_array(p->segments.p, size_t(p->num_segments) * 3 * sizeof(int64_t));
+  default:
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "unknown query selector");
+  }
+}
+
+} // extern "C"

@@ -1,0 +1,489 @@
+// inspect.cu — the GPU inspect phase (multiply_inspect).
+//
+// The reference's CPU multiply_inspect is a no-op
+// (include/spblas/algorithms/multiply_impl.hpp:19-29,105-116); this backend uses
+// the phase to analyse the sparsity structure once:
+//   1. row-length histogram (log2 bins), max row length, empty rows, and a
+//      monotonicity check of the offsets array;
+//   2. merge-path partition table: the (row, nnz) coordinate at which every
+//      fixed-size tile of the merged sequence (row ends ++ nonzeros) starts;
+//   3. CSC input: a row-major (CSR) image of the matrix built by a stable sort of
+//      the row indices, plus the permutation that gathers `values` at execute
+//      time (values may change between inspect and execute);
+//   4. SpMM: the list of row segments for rows longer than kSpmmSegment.
+// The CPU restatement these are compared against bit-exactly is oracle/spblas_oracle.c.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "plan.hpp"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kStatsWords = SPBLAS_B200_HIST_BINS + 4; // hist, max, flags, nseg, nsplit
+
+// ---------------------------------------------------------------------------
+// 1. row-length histogram
+// ---------------------------------------------------------------------------
+template <typename O>
+__global__ void __launch_bounds__(256)
+rowlen_hist_kernel(const O* __restrict__ rowptr, int64_t rows,
+                   unsigned long long* __restrict__ stats) {
+  __shared__ unsigned int s_hist[SPBLAS_B200_HIST_BINS];
+  __shared__ unsigned long long s_max;
+  __shared__ unsigned int s_bad;
+  if (threadIdx.x < SPBLAS_B200_HIST_BINS)
+    s_hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    s_max = 0;
+    s_bad = 0;
+  }
+  __syncthreads();
+
+  long long local_max = 0;
+  bool bad = false;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int64_t rows_padded = (rows + 31) / 32 * 32; // keep warps converged for match
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+       i < rows_padded; i += stride) {
+    int bin = -1;
+    if (i < rows) {
+      const long long a = (long long)rowptr[i];
+      const long long b = (long long)rowptr[i + 1];
+      const long long len = b - a;
+      if (len < 0) {
+        bad = true;
+        bin = 0;
+      } else {
+        bin = len == 0 ? 0 : 64 - __clzll(len);
+        if (bin > SPBLAS_B200_HIST_BINS - 1)
+          bin = SPBLAS_B200_HIST_BINS - 1;
+        local_max = len > local_max ? len : local_max;
+      }
+    }
+    // warp-aggregated shared-memory histogram: one atomic per distinct bin
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin >= 0 && (__ffs(peers) - 1) == int(threadIdx.x & 31))
+      atomicAdd(&s_hist[bin], __popc(peers));
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    long long o = __shfl_down_sync(0xffffffffu, local_max, off);
+    local_max = o > local_max ? o : local_max;
+  }
+  if ((threadIdx.x & 31) == 0)
+    atomicMax(&s_max, (unsigned long long)local_max);
+  if (bad)
+    atomicOr(&s_bad, 1u);
+  __syncthreads();
+  if (threadIdx.x < SPBLAS_B200_HIST_BINS && s_hist[threadIdx.x] != 0)
+    atomicAdd(&stats[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    atomicMax(&stats[SPBLAS_B200_HIST_BINS], s_max);
+    if (s_bad)
+      atomicOr(&stats[SPBLAS_B200_HIST_BINS + 1], 1ull);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// 2. merge-path partition (Merrill & Garland): list A = row-end offsets
+//    rowptr[1..rows] - base, list B = the natural numbers 0..nnz-1.  Tile t
+//    starts at diagonal t * tile_items.
+// ---------------------------------------------------------------------------
+template <typename O>
+__global__ void __launch_bounds__(256)
+merge_partition_kernel(const O* __restrict__ rowptr, int64_t rows, int64_t nnz,
+                       int64_t base, int tile_items, int64_t num_tiles,
+                       int64_t* __restrict__ tile_starts) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t > num_tiles)
+    return;
+  int64_t d = t * int64_t(tile_items);
+  const int64_t total = rows + nnz;
+  if (d > total)
+    d = total;
+  int64_t lo = d > nnz ? d - nnz : 0;
+  int64_t hi = d < rows ? d : rows;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int64_t row_end = int64_t(rowptr[mid + 1]) - base;
+    if (row_end <= d - 1 - mid)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  tile_starts[2 * t] = lo;
+  tile_starts[2 * t + 1] = base + (d - lo);
+}
+
+// ---------------------------------------------------------------------------
+// 3. CSC -> row-major image
+// ---------------------------------------------------------------------------
+// entry e of the CSC storage lives in column j: write j for every e in
+// [colptr[j], colptr[j+1]) (a "column of entry" expansion).
+template <typename I, typename O>
+__global__ void __launch_bounds__(256)
+expand_major_kernel(const O* __restrict__ ptr, int64_t majors, int64_t base,
+                    I* __restrict__ major_of_entry, O* __restrict__ entry_id,
+                    int64_t nnz) {
+  // one warp per major index; lanes stride over its entries
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t j = warp; j < majors; j += nwarps) {
+    const int64_t b = int64_t(ptr[j]) - base, e = int64_t(ptr[j + 1]) - base;
+    for (int64_t p = b + lane; p < e; p += 32) {
+      major_of_entry[p] = I(j);
+      entry_id[p] = O(p + base);
+    }
+  }
+}
+
+// rowptr of the sorted row keys: out[i] = lower_bound(keys, i)
+template <typename I, typename O>
+__global__ void __launch_bounds__(256)
+rowptr_from_sorted_kernel(const I* __restrict__ keys, int64_t nnz, int64_t rows,
+                          O* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i > rows)
+    return;
+  int64_t lo = 0, hi = nnz;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (int64_t(keys[mid]) < i)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  out[i] = O(lo);
+}
+
+template <typename I, typename O>
+__global__ void __launch_bounds__(256)
+gather_cols_kernel(const I* __restrict__ major_of_entry,
+                   const O* __restrict__ perm, int64_t base, int64_t nnz,
+                   I* __restrict__ out) {
+  const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p < nnz)
+    out[p] = major_of_entry[int64_t(perm[p]) - base];
+}
+
+// ---------------------------------------------------------------------------
+// 4. SpMM row segments: rows longer than `seg` are cut into ceil(len/seg) pieces.
+//    Pass 1 counts, pass 2 (after a host-side size check) fills in row order.
+// ---------------------------------------------------------------------------
+template <typename O>
+__global__ void __launch_bounds__(256)
+count_segments_kernel(const O* __restrict__ rowptr, int64_t rows, int64_t seg,
+                      unsigned long long* __restrict__ stats) {
+  unsigned long long nseg = 0, nsplit = 0;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < rows;
+       i += stride) {
+    const int64_t len = int64_t(rowptr[i + 1]) - int64_t(rowptr[i]);
+    if (len > seg) {
+      nseg += (unsigned long long)((len + seg - 1) / seg);
+      nsplit += 1;
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    nseg += __shfl_down_sync(0xffffffffu, nseg, off);
+    nsplit += __shfl_down_sync(0xffffffffu, nsplit, off);
+  }
+  if ((threadIdx.x & 31) == 0 && nseg) {
+    atomicAdd(&stats[SPBLAS_B200_HIST_BINS + 2], nseg);
+    atomicAdd(&stats[SPBLAS_B200_HIST_BINS + 3], nsplit);
+  }
+}
+
+int launch_ok(spblas_b200_plan* p, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return cuda_fail(p, e, what);
+  return SPBLAS_B200_SUCCESS;
+}
+
+template <typename O>
+int inspect_rows(spblas_b200_plan* p, const O* rowptr, int64_t rows, int flags) {
+  cudaStream_t s = p->stream;
+
+  // base offset and total: two scalars from the offsets array
+  O ends[2] = {0, 0};
+  if (rows > 0) {
+    B200_CUDA_TRY(p, cudaMemcpyAsync(&ends[0], rowptr, sizeof(O),
+                                     cudaMemcpyDeviceToHost, s));
+    B200_CUDA_TRY(p, cudaMemcpyAsync(&ends[1], rowptr + rows, sizeof(O),
+                                     cudaMemcpyDeviceToHost, s));
+    B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+  }
+  p->base = int64_t(ends[0]);
+  if (p->base < 0 || int64_t(ends[1]) - p->base != p->nnz)
+    return fail(p, SPBLAS_B200_INVALID_STRUCTURE,
+                "offsets array does not span nnz entries (ptr[last]-ptr[0] != nnz)");
+
+  int rc = reserve(p, p->stats, kStatsWords * sizeof(unsigned long long));
+  if (rc)
+    return rc;
+  auto* d_stats = static_cast<unsigned long long*>(p->stats.p);
+  B200_CUDA_TRY(p, cudaMemsetAsync(d_stats, 0,
+                                   kStatsWords * sizeof(unsigned long long), s));
+
+  const bool light = (flags & SPBLAS_B200_INSPECT_LIGHT) != 0;
+  p->have_hist = false;
+  if (!light && rows > 0) {
+    const int64_t want = (rows + 255) / 256;
+    const int grid = int(std::min<int64_t>(want, int64_t(p->num_sms) * 8));
+    rowlen_hist_kernel<O><<<grid, 256, 0, s>>>(rowptr, rows, d_stats);
+    if (int e = launch_ok(p, "rowlen_hist_kernel"))
+      return e;
+    count_segments_kernel<O><<<grid, 256, 0, s>>>(rowptr, rows, kSpmmSegment,
+                                                   d_stats);
+    if (int e = launch_ok(p, "count_segments_kernel"))
+      return e;
+  }
+
+  // merge-path partition table
+  p->tile_items = kSpmvTileItems;
+  const int64_t total = rows + p->nnz;
+  p->num_tiles = (total + p->tile_items - 1) / p->tile_items;
+  rc = reserve(p, p->tile_starts, size_t(p->num_tiles + 1) * 2 * sizeof(int64_t));
+  if (rc)
+    return rc;
+  rc = reserve(p, p->carry_row, size_t(p->num_tiles + 1) * sizeof(int64_t));
+  if (rc)
+    return rc;
+  rc = reserve(p, p->carry_val, size_t(p->num_tiles + 1) * 8);
+  if (rc)
+    return rc;
+  {
+    const int64_t nthreads = p->num_tiles + 1;
+    const int grid = int((nthreads + 255) / 256);
+    merge_partition_kernel<O><<<grid, 256, 0, s>>>(
+        rowptr, rows, p->nnz, p->base, p->tile_items, p->num_tiles,
+        static_cast<int64_t*>(p->tile_starts.p));
+    if (int e = launch_ok(p, "merge_partition_kernel"))
+      return e;
+  }
+
+  if (!light && rows > 0) {
+    unsigned long long h[kStatsWords];
+    B200_CUDA_TRY(p, cudaMemcpyAsync(h, d_stats, sizeof(h),
+                                     cudaMemcpyDeviceToHost, s));
+    B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+    if (h[SPBLAS_B200_HIST_BINS + 1] != 0)
+      return fail(p, SPBLAS_B200_INVALID_STRUCTURE,
+                  "offsets array is not monotonically non-decreasing");
+    for (int b = 0; b < SPBLAS_B200_HIST_BINS; ++b)
+      p->hist[b] = int64_t(h[b]);
+    p->max_row_len = int64_t(h[SPBLAS_B200_HIST_BINS]);
+    p->empty_rows = p->hist[0];
+    p->have_hist = true;
+    p->num_segments = int64_t(h[SPBLAS_B200_HIST_BINS + 2]);
+    p->num_split_rows = int64_t(h[SPBLAS_B200_HIST_BINS + 3]);
+  } else {
+    for (int b = 0; b < SPBLAS_B200_HIST_BINS; ++b)
+      p->hist[b] = 0;
+    p->max_row_len = 0;
+    p->empty_rows = 0;
+    p->num_segments = 0;
+    p->num_split_rows = 0;
+  }
+  return SPBLAS_B200_SUCCESS;
+}
+
+template <typename I, typename O>
+int build_row_major_image(spblas_b200_plan* p) {
+  // CSC storage: ptr = colptr[n+1], ind = rowind[nnz].  Stable radix sort of the
+  // row indices (keys) carrying the storage position (values) gives, for every
+  // row, its entries in ascending (column, storage) order — the same order in
+  // which the reference's column-major scatter (backend/algorithms.hpp:21-29)
+  // adds them into c[i].
+  cudaStream_t s = p->stream;
+  const int64_t nnz = p->nnz, rows = p->m, cols = p->n;
+  const O* colptr = static_cast<const O*>(p->user_ptr);
+  const I* rowind = static_cast<const I*>(p->user_ind);
+
+  O first = 0;
+  if (cols > 0) {
+    B200_CUDA_TRY(p, cudaMemcpyAsync(&first, colptr, sizeof(O),
+                                     cudaMemcpyDeviceToHost, s));
+    B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+  }
+  const int64_t base = int64_t(first);
+
+  int rc;
+  if ((rc = reserve(p, p->own_rowptr, size_t(rows + 1) * sizeof(O))))
+    return rc;
+  if ((rc = reserve(p, p->own_colind, size_t(std::max<int64_t>(nnz, 1)) * sizeof(I))))
+    return rc;
+  if ((rc = reserve(p, p->own_perm, size_t(std::max<int64_t>(nnz, 1)) * sizeof(O))))
+    return rc;
+  if ((rc = reserve(p, p->sort_tmp0, size_t(std::max<int64_t>(nnz, 1)) * sizeof(I))))
+    return rc; // column of entry
+  if ((rc = reserve(p, p->sort_tmp1, size_t(std::max<int64_t>(nnz, 1)) * sizeof(O))))
+    return rc; // entry id (unsorted)
+  if ((rc = reserve(p, p->sort_tmp2, size_t(std::max<int64_t>(nnz, 1)) * sizeof(I))))
+    return rc; // sorted keys
+
+  I* col_of_entry = static_cast<I*>(p->sort_tmp0.p);
+  O* entry_id = static_cast<O*>(p->sort_tmp1.p);
+  I* sorted_keys = static_cast<I*>(p->sort_tmp2.p);
+  O* perm = static_cast<O*>(p->own_perm.p);
+  O* t_rowptr = static_cast<O*>(p->own_rowptr.p);
+  I* t_colind = static_cast<I*>(p->own_colind.p);
+
+  if (nnz > 0) {
+    {
+      const int64_t warps = std::min<int64_t>(cols, int64_t(p->num_sms) * 64);
+      const int grid = int(std::max<int64_t>(1, (warps * 32 + 255) / 256));
+      expand_major_kernel<I, O><<<grid, 256, 0, s>>>(colptr, cols, base,
+                                                     col_of_entry, entry_id, nnz);
+      if (int e = launch_ok(p, "expand_major_kernel"))
+        return e;
+    }
+    if (nnz > int64_t(0x7fffffff))
+      return fail(p, SPBLAS_B200_NOT_SUPPORTED,
+                  "CSC inspect supports at most 2^31-1 stored entries");
+    int end_bit = 1;
+    while (end_bit < int(sizeof(I) * 8) && (int64_t(1) << end_bit) < rows)
+      ++end_bit;
+    size_t ws_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, ws_bytes, rowind + base,
+                                    sorted_keys, entry_id, perm, int(nnz), 0,
+                                    end_bit, s);
+    if ((rc = reserve(p, p->sort_ws, ws_bytes)))
+      return rc;
+    B200_CUDA_TRY(p, cub::DeviceRadixSort::SortPairs(
+                         p->sort_ws.p, ws_bytes, rowind + base, sorted_keys,
+                         entry_id, perm, int(nnz), 0, end_bit, s));
+    {
+      const int grid = int((nnz + 255) / 256);
+      gather_cols_kernel<I, O><<<grid, 256, 0, s>>>(col_of_entry, perm, base,
+                                                    nnz, t_colind);
+      if (int e = launch_ok(p, "gather_cols_kernel"))
+        return e;
+    }
+  }
+  {
+    const int grid = int((rows + 1 + 255) / 256);
+    rowptr_from_sorted_kernel<I, O><<<grid, 256, 0, s>>>(sorted_keys, nnz, rows,
+                                                         t_rowptr);
+    if (int e = launch_ok(p, "rowptr_from_sorted_kernel"))
+      return e;
+  }
+  p->csr_rowptr = t_rowptr;
+  p->csr_colind = t_colind;
+  p->csr_perm = perm;
+  p->csr_rows = rows;
+  p->csr_cols = cols;
+  return SPBLAS_B200_SUCCESS;
+}
+
+template <typename O>
+__global__ void __launch_bounds__(256)
+fill_segments_kernel(const O* __restrict__ rowptr, int64_t rows, int64_t seg,
+                     unsigned long long* __restrict__ cursor,
+                     int64_t* __restrict__ segments) {
+  // Deterministic order is restored by the host sort below; this kernel only
+  // needs every split row to emit its pieces contiguously.
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < rows;
+       i += stride) {
+    const int64_t b = int64_t(rowptr[i]), e = int64_t(rowptr[i + 1]);
+    const int64_t len = e - b;
+    if (len > seg) {
+      const unsigned long long n = (unsigned long long)((len + seg - 1) / seg);
+      unsigned long long at = atomicAdd(cursor, n);
+      for (unsigned long long q = 0; q < n; ++q) {
+        const int64_t sb = b + int64_t(q) * seg;
+        segments[3 * (at + q) + 0] = i;
+        segments[3 * (at + q) + 1] = sb;
+        segments[3 * (at + q) + 2] = sb + seg < e ? sb + seg : e;
+      }
+    }
+  }
+}
+
+template <typename O>
+int build_segments(spblas_b200_plan* p, const O* rowptr, int64_t rows) {
+  if (p->num_segments == 0)
+    return SPBLAS_B200_SUCCESS;
+  cudaStream_t s = p->stream;
+  int rc;
+  if ((rc = reserve(p, p->segments, size_t(p->num_segments) * 3 * sizeof(int64_t))))
+    return rc;
+  if ((rc = reserve(p, p->seg_counter, sizeof(unsigned long long))))
+    return rc;
+  B200_CUDA_TRY(p, cudaMemsetAsync(p->seg_counter.p, 0, sizeof(unsigned long long), s));
+  const int64_t want = (rows + 255) / 256;
+  const int grid = int(std::min<int64_t>(want, int64_t(p->num_sms) * 8));
+  fill_segments_kernel<O><<<grid, 256, 0, s>>>(
+      rowptr, rows, kSpmmSegment,
+      static_cast<unsigned long long*>(p->seg_counter.p),
+      static_cast<int64_t*>(p->segments.p));
+  if (int e = launch_ok(p, "fill_segments_kernel"))
+    return e;
+  // Split rows are rare (hubs of power-law matrices); order the list by
+  // (row, begin) on the host so that the layout — and with it the order in
+  // which partial rows are combined — is deterministic.
+  std::vector<int64_t> h(size_t(p->num_segments) * 3);
+  B200_CUDA_TRY(p, cudaMemcpyAsync(h.data(), p->segments.p,
+                                   h.size() * sizeof(int64_t),
+                                   cudaMemcpyDeviceToHost, s));
+  B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+  struct Seg {
+    int64_t r, b, e;
+  };
+  auto* segs = reinterpret_cast<Seg*>(h.data());
+  std::sort(segs, segs + p->num_segments, [](const Seg& a, const Seg& b) {
+    return a.r != b.r ? a.r < b.r : a.b < b.b;
+  });
+  B200_CUDA_TRY(p, cudaMemcpyAsync(p->segments.p, h.data(),
+                                   h.size() * sizeof(int64_t),
+                                   cudaMemcpyHostToDevice, s));
+  B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+  return SPBLAS_B200_SUCCESS;
+}
+
+template <typename I, typename O>
+int inspect_typed(spblas_b200_plan* p, int flags) {
+  if (p->format == SPBLAS_B200_CSC) {
+    if (int rc = build_row_major_image<I, O>(p))
+      return rc;
+  } else {
+    p->csr_rowptr = p->user_ptr;
+    p->csr_colind = p->user_ind;
+    p->csr_perm = nullptr;
+    p->csr_rows = p->m;
+    p->csr_cols = p->n;
+  }
+  const O* rowptr = static_cast<const O*>(p->csr_rowptr);
+  if (int rc = inspect_rows<O>(p, rowptr, p->csr_rows, flags))
+    return rc;
+  if (int rc = build_segments<O>(p, rowptr, p->csr_rows))
+    return rc;
+  return SPBLAS_B200_SUCCESS;
+}
+
+} // namespace
+
+int inspect_structure(spblas_b200_plan* p, int flags) {
+  const bool i64 = p->idx_type == SPBLAS_B200_I64;
+  const bool o64 = p->off_type == SPBLAS_B200_I64;
+  int rc;
+  if (!i64 && !o64)
+    rc = inspect_typed<int32_t, int32_t>(p, flags);
+  else if (!i64 && o64)
+    rc = inspect_typed<int32_t, int64_t>(p, flags);
+  else if (i64 && !o64)
+    rc = inspect_typed<int64_t, int32_t>(p, flags);
+  else
+    rc = inspect_typed<int64_t, int64_t>(p, flags);
+  return rc;
+}
+
+} // namespace b200

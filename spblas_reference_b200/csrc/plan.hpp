@@ -1,0 +1,124 @@
+// plan.hpp — the inspect-phase state behind `spblas_b200_plan` (opaque in the C ABI).
+//
+// It plays the role of __cusparse::spmv_state_t
+// (reference: include/spblas/vendor/cusparse/detail/spmv_state_t.hpp:11-52) but
+// owns real metadata: the merge-path partition table, the row-length histogram,
+// the CSR image of a CSC matrix and the carry workspace, so that execute never
+// allocates (the reference's cuSPARSE wrapper mallocs per call,
+// vendor/cusparse/spmv_impl.hpp:74-89).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "../../include/spblas_b200.h"
+
+namespace b200 {
+
+// ---- tiling constants shared by inspect and execute -------------------------
+constexpr int kSpmvThreads = 256;
+// merge items (row ends + nonzeros) per CTA tile
+constexpr int kSpmvTileItems = 2048;
+// SpMM: rows longer than this are cut into segments of this many nonzeros
+constexpr int64_t kSpmmSegment = 4096;
+
+// SpMV kernel variants (reported by SPBLAS_B200_Q_SPMV_VARIANT)
+enum SpmvVariant : int {
+  kVariantAuto = -1,
+  kVariantMergeTile = 0, // merge-path tiles, smem-staged products, adaptive row reduce
+};
+
+struct DeviceBuffer {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+} // namespace b200
+
+struct spblas_b200_plan {
+  cudaStream_t stream = nullptr;
+  int device = 0;
+  int num_sms = 148;
+
+  // ---- structure as given by the caller (not owned) -------------------------
+  bool inspected = false;
+  int format = SPBLAS_B200_CSR;
+  int off_type = SPBLAS_B200_I32;
+  int idx_type = SPBLAS_B200_I32;
+  int64_t m = 0, n = 0, nnz = 0; // logical shape of A
+  const void* user_ptr = nullptr;
+  const void* user_ind = nullptr;
+  int64_t k_hint = 1;
+
+  // ---- effective CSR structure the kernels run on ---------------------------
+  // CSR input: aliases user_ptr/user_ind, perm == nullptr.
+  // CSC input: owned row-major image (csr_rows = m, csr_cols = n) + value permutation.
+  const void* csr_rowptr = nullptr;
+  const void* csr_colind = nullptr;
+  const void* csr_perm = nullptr;
+  int64_t csr_rows = 0, csr_cols = 0;
+  int64_t base = 0; // rowptr[0] of the effective structure
+  b200::DeviceBuffer own_rowptr, own_colind, own_perm, sort_tmp0, sort_tmp1,
+      sort_tmp2, sort_ws;
+
+  // ---- merge-path partition --------------------------------------------------
+  int tile_items = b200::kSpmvTileItems;
+  int64_t num_tiles = 0;
+  b200::DeviceBuffer tile_starts; // int64 (row, nnz) pairs, num_tiles + 1 entries
+  b200::DeviceBuffer carry_row;   // int64 per tile
+  b200::DeviceBuffer carry_val;   // 8 bytes per tile
+
+  // ---- SpMM segments ---------------------------------------------------------
+  int64_t num_segments = 0;        // 0: no row is split
+  int64_t num_split_rows = 0;
+  b200::DeviceBuffer segments;     // int64 (row, begin, end) triples
+  b200::DeviceBuffer seg_partial;  // partial C rows of split rows (num_segments x k)
+  b200::DeviceBuffer seg_counter;  // int64 scratch
+
+  // ---- statistics -------------------------------------------------------------
+  bool have_hist = false;
+  int64_t hist[SPBLAS_B200_HIST_BINS] = {0};
+  int64_t max_row_len = 0;
+  int64_t empty_rows = 0;
+  b200::DeviceBuffer stats; // device scratch for hist/max/flags
+
+  int forced_variant = -1;
+  int spmv_variant = b200::kVariantMergeTile;
+  int spmm_variant = 0;
+  int64_t last_launches = 0;
+  int64_t total_launches = 0;
+
+  std::string err;
+};
+
+namespace b200 {
+
+// status helpers (cabi.cu)
+int fail(spblas_b200_plan* p, int status, const std::string& msg);
+int cuda_fail(spblas_b200_plan* p, cudaError_t e, const char* what);
+int reserve(spblas_b200_plan* p, DeviceBuffer& b, size_t bytes);
+void release(DeviceBuffer& b);
+
+#define B200_CUDA_TRY(plan, expr)                                              \
+  do {                                                                         \
+    cudaError_t e__ = (expr);                                                  \
+    if (e__ != cudaSuccess)                                                    \
+      return ::b200::cuda_fail((plan), e__, #expr);                            \
+  } while (0)
+
+// inspect.cu
+int inspect_structure(spblas_b200_plan* p, int flags);
+// spmv.cu
+int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
+             const void* values, const void* x, void* y);
+// spmm.cu
+int run_spmm(spblas_b200_plan* p, int val_type, const void* alpha,
+             const void* values, const void* B, int64_t ldb, void* C,
+             int64_t ldc, int64_t k);
+
+inline size_t type_size_idx(int t) { return t == SPBLAS_B200_I64 ? 8 : 4; }
+inline size_t type_size_val(int t) { return t == SPBLAS_B200_F64 ? 8 : 4; }
+
+} // namespace b200

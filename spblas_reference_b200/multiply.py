@@ -1,0 +1,274 @@
+"""multiply / multiply_inspect / multiply_execute — host-side mirror of the reference's
+operator interface for the sparse-times-dense path, calling the sm_100a kernels through
+the C ABI (include/spblas_b200.h).
+
+Reference interface mirrored (names, argument meaning, error behaviour):
+  multiply(a, x, y), multiply(info, a, x, y)             algorithms/multiply.hpp:15-26
+  multiply_inspect(a, x, y), multiply_inspect(info, ..)  algorithms/multiply.hpp:9-13,29-33
+  multiply_execute(info, a, x, y)                        README.md:33-47 (documented spelling)
+  operation_info_t                                       detail/operation_info_t.hpp:28-104
+Argument decoding follows vendor/cusparse/spmv_impl.hpp:29-40: peel views, reject
+conjugated views, alpha = product of scaling factors, beta = 0.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .views import (csc_view, csr_view, get_scaling_factor, get_ultimate_base, index_type,
+                    is_conjugated, value_type, _check_1d_cuda)
+
+_NP = {_cabi.F32: np.float32, _cabi.F64: np.float64, _cabi.S32: np.int32}
+
+
+def _stream_ptr(device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+class operation_info_t:
+    """Result of multiply_inspect: owns the backend plan (RAII, move-only in C++:
+    include/spblas/vendor/b200/operation_state_t.hpp).  result_shape / result_nnz mirror
+    detail/operation_info_t.hpp:30-36."""
+
+    def __init__(self):
+        self._plan = C.c_void_p()
+        self._device = None
+        self._sig = None
+        self.result_shape = (0, 0)
+        self.result_nnz = 0
+
+    # -- plan lifetime ---------------------------------------------------------------
+    def _ensure(self, device) -> C.c_void_p:
+        if not self._plan:
+            with torch.cuda.device(device):
+                st = _cabi.lib().spblas_b200_plan_create(C.byref(self._plan), _stream_ptr(device))
+            _cabi.raise_for_status(st, "plan_create")
+            self._device = device
+        return self._plan
+
+    def close(self):
+        if self._plan:
+            _cabi.lib().spblas_b200_plan_destroy(self._plan)
+            self._plan = C.c_void_p()
+            self._sig = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self) -> str:
+        return _cabi.lib().spblas_b200_last_error(self._plan).decode()
+
+    # -- metadata (SPBLAS_B200_Q_*) ---------------------------------------------------
+    def _query_scalar(self, what: int) -> int:
+        out = C.c_int64(0)
+        st = _cabi.lib().spblas_b200_plan_query(self._plan, what, C.byref(out), 8, None)
+        _cabi.raise_for_status(st, self._err())
+        return int(out.value)
+
+    def _query_array(self, what: int, dtype) -> np.ndarray:
+        need = C.c_size_t(0)
+        st = _cabi.lib().spblas_b200_plan_query(self._plan, what, None, 0, C.byref(need))
+        _cabi.raise_for_status(st, self._err())
+        buf = np.zeros(need.value // np.dtype(dtype).itemsize, dtype=dtype)
+        if need.value:
+            st = _cabi.lib().spblas_b200_plan_query(self._plan, what,
+                                                    buf.ctypes.data_as(C.c_void_p),
+                                                    need.value, None)
+            _cabi.raise_for_status(st, self._err())
+        return buf
+
+    @property
+    def num_tiles(self): return self._query_scalar(_cabi.Q_NUM_TILES)
+    @property
+    def tile_items(self): return self._query_scalar(_cabi.Q_TILE_ITEMS)
+    @property
+    def tile_starts(self): return self._query_array(_cabi.Q_TILE_STARTS, np.int64).reshape(-1, 2)
+    @property
+    def rowlen_hist(self): return self._query_array(_cabi.Q_ROWLEN_HIST, np.int64)
+    @property
+    def max_row_len(self): return self._query_scalar(_cabi.Q_MAX_ROW_LEN)
+    @property
+    def empty_rows(self): return self._query_scalar(_cabi.Q_EMPTY_ROWS)
+    @property
+    def last_launches(self): return self._query_scalar(_cabi.Q_LAST_LAUNCHES)
+    @property
+    def total_launches(self): return self._query_scalar(_cabi.Q_TOTAL_LAUNCHES)
+    @property
+    def num_segments(self): return self._query_scalar(_cabi.Q_NUM_SEGMENTS)
+    @property
+    def segments(self): return self._query_array(_cabi.Q_SEGMENTS, np.int64).reshape(-1, 3)
+    @property
+    def spmv_variant(self): return self._query_scalar(_cabi.Q_SPMV_VARIANT)
+    @property
+    def spmm_variant(self): return self._query_scalar(_cabi.Q_SPMM_VARIANT)
+
+    def effective_csr(self, off_dtype, idx_dtype):
+        """(rowptr, colind, perm) of the row-major structure the kernels run on."""
+        return (self._query_array(_cabi.Q_CSR_ROWPTR, off_dtype),
+                self._query_array(_cabi.Q_CSR_COLIND, idx_dtype),
+                self._query_array(_cabi.Q_CSR_PERM, off_dtype))
+
+
+# ---------------------------------------------------------------------------------------
+def _decode_matrix(a):
+    if is_conjugated(a):
+        raise RuntimeError("b200 backend does not support conjugated views.")
+    base = get_ultimate_base(a)
+    if isinstance(base, csr_view):
+        fmt, ptr, ind = _cabi.CSR, base.rowptr, base.colind
+    elif isinstance(base, csc_view):
+        fmt, ptr, ind = _cabi.CSC, base.colptr, base.rowind
+    else:
+        raise TypeError("multiply: A must be a csr_view or csc_view (possibly wrapped)")
+    _check_1d_cuda(base.values, "A.values")
+    _check_1d_cuda(ptr, "A offsets")
+    _check_1d_cuda(ind, "A indices")
+    return base, fmt, ptr, ind
+
+
+def _is_matrix(t) -> bool:
+    return isinstance(t, torch.Tensor) and t.dim() == 2
+
+
+def _check_shapes(a_base, x_base, y):
+    m, n = a_base.shape
+    if _is_matrix(y) != _is_matrix(x_base):
+        raise TypeError("multiply: x and y must both be vectors or both be matrices")
+    if _is_matrix(y):
+        # reference multiply_impl.hpp:70-75
+        if m != y.shape[0] or x_base.shape[1] != y.shape[1] or n != x_base.shape[0]:
+            raise ValueError("multiply: matrix dimensions are incompatible.")
+    else:
+        # reference multiply_impl.hpp:37-41
+        if m != y.shape[0] or n != x_base.shape[0]:
+            raise ValueError("multiply: matrix and vector dimensions are incompatible.")
+
+
+def _row_major(t: torch.Tensor, what: str):
+    """mdspan_row_major contract (detail/mdspan.hpp:38-41): unit column stride; the row
+    stride is the leading dimension."""
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise RuntimeError(f"multiply: {what} must be row-major (layout_right)")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+    return int(max(ld, t.shape[1]))
+
+
+def _signature(fmt, a_base, ptr, ind):
+    return (fmt, a_base.shape, a_base.nnz, ptr.data_ptr(), ind.data_ptr(), ptr.dtype, ind.dtype)
+
+
+def _inspect(info: operation_info_t, a, x, y, flags=_cabi.INSPECT_DEFAULT):
+    a_base, fmt, ptr, ind = _decode_matrix(a)
+    x_base = get_ultimate_base(x)
+    _check_shapes(a_base, x_base, y)
+    dev = a_base.values.device
+    plan = info._ensure(dev)
+    k_hint = int(y.shape[1]) if _is_matrix(y) else 1
+    with torch.cuda.device(dev):
+        _cabi.lib().spblas_b200_plan_set_stream(plan, _stream_ptr(dev))
+        st = _cabi.lib().spblas_b200_inspect(
+            plan, fmt, a_base.shape[0], a_base.shape[1], a_base.nnz, ptr.data_ptr(),
+            ind.data_ptr(), index_type(ptr), index_type(ind), k_hint, flags)
+    _cabi.raise_for_status(st, info._err())
+    info._sig = _signature(fmt, a_base, ptr, ind)
+    info.result_shape = tuple(y.shape) if _is_matrix(y) else (int(y.shape[0]), 1)
+    info.result_nnz = int(y.numel())
+
+
+def multiply_inspect(*args):
+    """multiply_inspect(a, x, y) -> operation_info_t, or multiply_inspect(info, a, x, y).
+    Runs the GPU inspect phase: row-length histogram, merge-path partition, CSC image,
+    SpMM row segments (csrc/inspect.cu)."""
+    if len(args) == 3:
+        info = operation_info_t()
+        _inspect(info, *args)
+        return info
+    if len(args) == 4 and isinstance(args[0], operation_info_t):
+        _inspect(args[0], *args[1:])
+        return None
+    raise TypeError("multiply_inspect(a, x, y) or multiply_inspect(info, a, x, y)")
+
+
+def _execute(info: Optional[operation_info_t], a, x, y):
+    a_base, fmt, ptr, ind = _decode_matrix(a)
+    if is_conjugated(x) or is_conjugated(y):
+        raise RuntimeError("b200 backend does not support conjugated views.")
+    x_base = get_ultimate_base(x)
+    if not isinstance(y, torch.Tensor):
+        raise TypeError("multiply: the output must be a plain tensor (no views)")
+    _check_shapes(a_base, x_base, y)
+    for t, what in ((x_base, "x"), (y, "y")):
+        if not t.is_cuda:
+            raise RuntimeError(f"{what} must live in device memory (no CPU path)")
+    vt = value_type(a_base.values)
+    if x_base.dtype != a_base.values.dtype or y.dtype != a_base.values.dtype:
+        raise RuntimeError("b200 backend needs A, x and y of one scalar type")
+    alpha = get_scaling_factor(a, x)
+    alpha_np = np.array([1 if alpha is None else alpha], dtype=_NP[vt])
+    alpha_p = alpha_np.ctypes.data_as(C.c_void_p)
+    dev = a_base.values.device
+    L = _cabi.lib()
+    m, n = a_base.shape
+
+    with torch.cuda.device(dev):
+        stream = _stream_ptr(dev)
+        if info is None:
+            # no operation_info_t: one-shot entry points (thread-local cached plan,
+            # light re-inspect every call)
+            if _is_matrix(y):
+                st = L.spblas_b200_spmm_once(
+                    stream, fmt, m, n, a_base.nnz, ptr.data_ptr(), ind.data_ptr(),
+                    index_type(ptr), index_type(ind), vt, alpha_p, a_base.values.data_ptr(),
+                    x_base.data_ptr(), _row_major(x_base, "B"), y.data_ptr(),
+                    _row_major(y, "C"), int(y.shape[1]))
+            else:
+                _check_1d_cuda(x_base, "x")
+                _check_1d_cuda(y, "y")
+                st = L.spblas_b200_spmv_once(
+                    stream, fmt, m, n, a_base.nnz, ptr.data_ptr(), ind.data_ptr(),
+                    index_type(ptr), index_type(ind), vt, alpha_p, a_base.values.data_ptr(),
+                    x_base.data_ptr(), y.data_ptr())
+            _cabi.raise_for_status(st, L.spblas_b200_last_error_once().decode())
+            return
+
+        if info._sig != _signature(fmt, a_base, ptr, ind):
+            # first use of this info, or a different matrix: inspect lazily, like
+            # vendor/cusparse/spmv_impl.hpp:43-55 creates its state on first use
+            _inspect(info, a, x, y)
+        plan = info._plan
+        L.spblas_b200_plan_set_stream(plan, stream)
+        if _is_matrix(y):
+            st = L.spblas_b200_spmm(plan, vt, alpha_p, a_base.values.data_ptr(),
+                                    x_base.data_ptr(), _row_major(x_base, "B"), y.data_ptr(),
+                                    _row_major(y, "C"), int(y.shape[1]))
+        else:
+            _check_1d_cuda(x_base, "x")
+            _check_1d_cuda(y, "y")
+            st = L.spblas_b200_spmv(plan, vt, alpha_p, a_base.values.data_ptr(),
+                                    x_base.data_ptr(), y.data_ptr())
+        _cabi.raise_for_status(st, info._err())
+
+
+def multiply(*args):
+    """multiply(a, x, y) or multiply(info, a, x, y): y = alpha * A * x (SpMV) or
+    C = alpha * A * B (SpMM, row-major 2-D tensors); y / C is overwritten (beta = 0)."""
+    if len(args) == 3:
+        return _execute(None, *args)
+    if len(args) == 4 and isinstance(args[0], operation_info_t):
+        return _execute(*args)
+    raise TypeError("multiply(a, x, y) or multiply(info, a, x, y)")
+
+
+def multiply_execute(info: operation_info_t, a, x, y):
+    """The execute phase under the name the reference documents (README.md:46,
+    notes/spmv.hpp:20-22); identical to multiply(info, a, x, y)."""
+    if not isinstance(info, operation_info_t):
+        raise TypeError("multiply_execute(info, a, x, y)")
+    return _execute(info, a, x, y)

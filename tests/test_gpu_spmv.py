@@ -1,0 +1,290 @@
+"""GPU parity tests for SpMV: the CUDA path (through the host API -> C ABI) against the
+oracle, the committed golden vectors of the real reference, and — at BASELINE sizes —
+size-independent properties.  Re-hosts the bodies of the reference's
+test/gtest/device/spmv_test.cpp:11-146 (thrust_CsrView SpMV / SpMV_Ascaled / SpMV_BScaled)
+and adds what the reference lacks: fp64, int32 scalars, int64 offsets, empty
+rows, duplicates, very long rows, inspect reuse, multiply_execute, structure queries."""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+import spblas_reference_b200 as sb
+from spblas_reference_b200 import generators as G
+from conftest import DIMS, GOLDEN, golden
+from helpers import (assert_rows_within_bound, csc_on_device, csr_on_device, dev, gpu_spmv)
+
+pytestmark = pytest.mark.gpu
+ALPHAS = [-10, 1, 5]
+
+
+@pytest.mark.parametrize("dims", DIMS)
+def test_reference_device_spmv_tests(cuda, oracle, dims):
+    """thrust_CsrView.SpMV / SpMV_Ascaled / SpMV_BScaled on the reference's own fixtures,
+    judged by the reference's own EXPECT_EQ_ and against the real reference's output."""
+    g = golden(*dims)
+    m, n, _ = dims
+    v, rp, ci = g["csr_values"], g["csr_ptr"], g["csr_ind"]
+    a = csr_on_device(v, rp, ci, (m, n))
+    x = np.ones(n, np.float32)
+    y = gpu_spmv(a, x, m, np.float32)
+    assert oracle.expect_eq_tolerance(g["csr_spmv"], y).all()
+    assert_rows_within_bound(y, g["csr_spmv"], rp, oracle.abs_rowsum(rp, ci, v, x), "spmv")
+    for alpha in ALPHAS:
+        ya = gpu_spmv(a, x, m, np.float32, alpha_a=alpha)
+        assert oracle.expect_eq_tolerance(g[f"csr_spmv_ascaled_{alpha}"], ya).all()
+        yb = gpu_spmv(a, x, m, np.float32, alpha_x=alpha)
+        assert oracle.expect_eq_tolerance(g[f"csr_spmv_bscaled_{alpha}"], yb).all()
+        bound = oracle.abs_rowsum(rp, ci, v, x, alpha)
+        assert_rows_within_bound(ya, g[f"csr_spmv_ascaled_{alpha}"], rp, bound, "ascaled")
+        assert_rows_within_bound(yb, g[f"csr_spmv_bscaled_{alpha}"], rp, bound, "bscaled")
+
+
+def test_probe_semantics_on_gpu(cuda):
+    p = np.load(f"{GOLDEN}/probe_3x4.npz")
+    rp, ci, v, x = p["rowptr"], p["colind"], p["values"], p["x"]
+    a = csr_on_device(v, rp, ci, (3, 4))
+    assert gpu_spmv(a, x, 3, np.float32).tolist() == [140.0, 0.0, 160.0]   # stale NaN discarded
+    xinf = x.copy()
+    xinf[1] = np.inf                                                      # never referenced
+    assert gpu_spmv(a, xinf, 3, np.float32).tolist() == [140.0, 0.0, 160.0]
+    assert gpu_spmv(a, x, 3, np.float32, alpha_a=2, alpha_x=3).tolist() == [840.0, 0.0, 960.0]
+    ai = csr_on_device(v.astype(np.int32), rp, ci, (3, 4))
+    assert gpu_spmv(ai, x.astype(np.int32), 3, np.int32).tolist() == [140, 0, 160]
+    # transposed(csr) behaves as the csc over the same arrays
+    t = sb.transposed(a)
+    assert gpu_spmv(t, np.ones(3, np.float32), 4, np.float32).tolist() == [2.0, 0.0, 4.0, 4.0]
+
+
+def _random_csr(rng, m, n, kind, vt, it, ot):
+    if kind == "short":
+        lens = rng.integers(0, 12, size=m)
+    elif kind == "mixed":
+        lens = rng.integers(0, 6, size=m)
+        lens[rng.integers(0, m, size=max(1, m // 50))] = rng.integers(65, 700, size=max(1, m // 50))
+    elif kind == "hub":
+        lens = rng.integers(0, 4, size=m)
+        lens[m // 3] = 9000          # spans > 4 tiles of 2048 items
+        lens[m - 1] = 2500
+        lens[0] = 2049
+    elif kind == "long":
+        lens = rng.integers(100, 400, size=m)
+    elif kind == "empty":
+        lens = np.zeros(m, dtype=np.int64)
+    else:
+        raise ValueError(kind)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(ot)
+    nnz = int(rp[-1])
+    ci = rng.integers(0, n, size=nnz).astype(it)       # unsorted, duplicates legal
+    if vt == np.int32:
+        v = rng.integers(-9, 10, size=nnz).astype(vt)
+        x = rng.integers(-9, 10, size=n).astype(vt)
+    else:
+        v = rng.standard_normal(nnz).astype(vt)
+        x = rng.standard_normal(n).astype(vt)
+    return v, rp, ci, x
+
+
+@pytest.mark.parametrize("kind", ["short", "mixed", "hub", "long", "empty"])
+@pytest.mark.parametrize("types", [(np.float32, np.int32, np.int32),
+                                   (np.float64, np.int32, np.int32),
+                                   (np.int32, np.int32, np.int32),
+                                   (np.float64, np.int32, np.int64),
+                                   (np.float32, np.int64, np.int64)])
+def test_spmv_vs_oracle(cuda, oracle, kind, types):
+    vt, it, ot = types
+    rng = np.random.default_rng(zlib.crc32(f"{kind}{vt.__name__}{ot.__name__}".encode()))
+    m, n = 3001, 1777
+    v, rp, ci, x = _random_csr(rng, m, n, kind, vt, it, ot)
+    a = csr_on_device(v, rp, ci, (m, n))
+    alpha = 3 if vt == np.int32 else 0.75
+    for kw in ({}, {"alpha_a": alpha}):
+        y_ref = oracle.spmv("csr", (m, n), rp, ci, v, x, **kw)
+        bound = None if vt == np.int32 else oracle.abs_rowsum(rp, ci, v, x, kw.get("alpha_a", 1.0))
+        # no-info path (light inspect per call), inspected path, multiply_execute spelling
+        info = sb.multiply_inspect(a, dev(x), torch.empty(m, dtype=dev(x).dtype, device="cuda"))
+        for y in (gpu_spmv(a, x, m, vt, **kw), gpu_spmv(a, x, m, vt, info=info, **kw),
+                  gpu_spmv(a, x, m, vt, info=info, execute=True, **kw)):
+            assert_rows_within_bound(y, y_ref, rp, bound, f"{kind} {vt.__name__}")
+        info.close()
+
+
+@pytest.mark.parametrize("kind", ["short", "hub", "empty"])
+def test_inspect_structures_bit_exact(cuda, oracle, kind):
+    """Row-length histogram, merge-path partition table and SpMM segments produced by the
+    GPU inspect equal the CPU restatement exactly."""
+    rng = np.random.default_rng(11)
+    m, n = 5000, 4000
+    v, rp, ci, x = _random_csr(rng, m, n, kind, np.float32, np.int32, np.int32)
+    a = csr_on_device(v, rp, ci, (m, n))
+    info = sb.multiply_inspect(a, dev(x), torch.empty(m, device="cuda"))
+    hist, mx = oracle.rowlen_hist(rp)
+    assert np.array_equal(info.rowlen_hist, hist)
+    assert info.max_row_len == mx and info.empty_rows == hist[0]
+    tile = info.tile_items
+    want = oracle.merge_partition(rp, tile)
+    assert info.num_tiles == len(want) - 1
+    assert np.array_equal(info.tile_starts, want)
+    segs = oracle.row_segments(rp, 4096)
+    assert info.num_segments == len(segs)
+    if len(segs):
+        assert np.array_equal(info.segments, segs)
+    assert info.last_launches == 0
+    y = torch.empty(m, device="cuda")
+    sb.multiply(info, a, dev(x), y)
+    assert info.last_launches >= 1 and info.total_launches == info.last_launches
+    info.close()
+
+
+def test_values_may_change_between_executes(cuda, oracle):
+    rng = np.random.default_rng(2)
+    m, n = 2000, 2000
+    v, rp, ci, x = _random_csr(rng, m, n, "short", np.float64, np.int32, np.int32)
+    a = csr_on_device(v, rp, ci, (m, n))
+    xd, y = dev(x), torch.empty(m, dtype=torch.float64, device="cuda")
+    info = sb.multiply_inspect(a, xd, y)
+    for rep in range(3):
+        v2 = rng.standard_normal(len(v))
+        a.values.copy_(dev(v2))
+        sb.multiply_execute(info, a, xd, y)
+        assert_rows_within_bound(y.cpu().numpy(), oracle.spmv("csr", (m, n), rp, ci, v2, x), rp,
+                                 oracle.abs_rowsum(rp, ci, v2, x), "values changed")
+
+
+def test_shard_with_nonzero_base_and_unaligned_pointers(cuda, oracle):
+    """A row block of a larger matrix keeps the global rowptr values (base != 0) and slices
+    of the global arrays whose addresses are not 16-byte aligned."""
+    rng = np.random.default_rng(4)
+    m, n = 4000, 3000
+    v, rp, ci, x = _random_csr(rng, m, n, "mixed", np.float32, np.int32, np.int32)
+    y_ref = oracle.spmv("csr", (m, n), rp, ci, v, x)
+    vd, rpd, cid, xd = dev(v), dev(rp), dev(ci), dev(x)
+    r0, r1 = 1001, 3333
+    # views index values/colind with the absolute offsets, exactly like
+    # backend/view_customizations.hpp:48-66 does
+    a = sb.csr_view(vd, rpd[r0:r1 + 1], cid, (r1 - r0, n), int(rp[r1] - rp[r0]))
+    y = torch.full((r1 - r0,), float("nan"), device="cuda")
+    info = sb.multiply_inspect(a, xd, y)
+    sb.multiply(info, a, xd, y)
+    bound = oracle.abs_rowsum(rp, ci, v, x)[r0:r1]
+    assert_rows_within_bound(y.cpu().numpy(), y_ref[r0:r1], rp[r0:r1 + 1], bound, "shard")
+    # unaligned: shift every array by one element
+    pad = lambda t: torch.cat([t[:1], t])[1:]
+    a2 = sb.csr_view(pad(vd), rpd, pad(cid), (m, n), int(rp[-1]))
+    assert a2.values.data_ptr() % 16 != 0
+    y2 = torch.empty(m, device="cuda")
+    sb.multiply(a2, xd, y2)
+    assert_rows_within_bound(y2.cpu().numpy(), y_ref, rp, oracle.abs_rowsum(rp, ci, v, x), "unaligned")
+
+
+def test_errors_match_reference(cuda):
+    p = np.load(f"{GOLDEN}/probe_3x4.npz")
+    a = csr_on_device(p["values"], p["rowptr"], p["colind"], (3, 4))
+    with pytest.raises(ValueError, match="matrix and vector dimensions are incompatible"):
+        sb.multiply(a, torch.zeros(5, device="cuda"), torch.zeros(3, device="cuda"))
+    with pytest.raises(RuntimeError):
+        sb.multiply(a, torch.zeros(4, device="cuda", dtype=torch.float64),
+                    torch.zeros(3, device="cuda"))
+    bad = sb.csr_view(a.values, dev(np.array([0, 3, 2, 4], np.int32)), a.colind, (3, 4), 4)
+    with pytest.raises(RuntimeError, match="monoton"):
+        sb.multiply_inspect(bad, torch.zeros(4, device="cuda"), torch.zeros(3, device="cuda"))
+
+
+def test_zero_sized(cuda):
+    a = sb.csr_view(torch.zeros(0, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda"),
+                    torch.zeros(0, dtype=torch.int32, device="cuda"), (0, 5), 0)
+    sb.multiply(a, torch.zeros(5, device="cuda"), torch.zeros(0, device="cuda"))
+    a = sb.csr_view(torch.zeros(0, device="cuda"), torch.zeros(8, dtype=torch.int32, device="cuda"),
+                    torch.zeros(0, dtype=torch.int32, device="cuda"), (7, 5), 0)
+    y = torch.full((7,), float("nan"), device="cuda")
+    sb.multiply(a, torch.zeros(5, device="cuda"), y)
+    assert y.cpu().tolist() == [0.0] * 7
+
+
+# ---- BASELINE-size cases: generated on the device, checked against the oracle run on the
+# host copy (the C oracle does 80M nonzeros in well under a second) and by properties ------
+def test_c1_uniform_random_full_size(cuda, oracle):
+    m = n = 1_000_000
+    v, rp, ci, shape = G.uniform_random_csr(m, n, 10, seed=0, dtype=torch.float32, device=cuda)
+    a = sb.csr_view(v, rp, ci, shape, int(ci.numel()))
+    x = torch.ones(n, device=cuda)
+    y = torch.empty(m, device=cuda)
+    info = sb.multiply_inspect(a, x, y)
+    sb.multiply(info, sb.scaled(1.2, a), x, y)                  # examples/simple_spmv.cpp:44-48
+    vh, rph, cih, xh = v.cpu().numpy(), rp.cpu().numpy(), ci.cpu().numpy(), x.cpu().numpy()
+    y_ref = oracle.spmv("csr", shape, rph, cih, vh, xh, alpha_a=1.2)
+    assert_rows_within_bound(y.cpu().numpy(), y_ref, rph, oracle.abs_rowsum(rph, cih, vh, xh, 1.2), "C1")
+
+
+def test_c2_poisson_known_answer_and_iteration(cuda, oracle):
+    g = 1024                                                   # full 4096 runs in bench.py
+    v, rp, ci, shape = G.poisson2d_csr(g, torch.float64, cuda)
+    n = g * g
+    a = sb.csr_view(v, rp, ci, shape, int(ci.numel()))
+    x = torch.ones(n, dtype=torch.float64, device=cuda)
+    y = torch.empty(n, dtype=torch.float64, device=cuda)
+    info = sb.multiply_inspect(a, x, y)
+    sb.multiply(info, a, x, y)
+    # A * 1 = 4 - (number of neighbours): exact small integers
+    i, j = torch.arange(n, device=cuda) // g, torch.arange(n, device=cuda) % g
+    want = 4.0 - ((i > 0).double() + (i < g - 1).double() + (j > 0).double() + (j < g - 1).double())
+    assert torch.equal(y, want)
+    # iterated y -> x with scaled(1/8, a), checked per iteration against the oracle fed the
+    # same input (not compounded), SURVEY §8d
+    x = G.dense_uniform((n,), 1, torch.float64, cuda)
+    vh, rph, cih = v.cpu().numpy(), rp.cpu().numpy(), ci.cpu().numpy()
+    for it in range(3):
+        sb.multiply_execute(info, sb.scaled(0.125, a), x, y)
+        xh = x.cpu().numpy()
+        y_ref = oracle.spmv("csr", shape, rph, cih, vh, xh, alpha_a=0.125)
+        assert_rows_within_bound(y.cpu().numpy(), y_ref, rph,
+                                 oracle.abs_rowsum(rph, cih, vh, xh, 0.125), f"C2 it{it}")
+        x, y = y, x
+
+
+def test_c4_rmat_skewed_rows(cuda, oracle):
+    scale = 18                                                 # scale 24 runs in bench.py
+    v, rp, ci, shape = G.rmat_csr(scale, 16, seed=24, dtype=torch.float32, device=cuda)
+    m, n = shape
+    a = sb.csr_view(v, rp, ci, shape, int(ci.numel()))
+    x = G.dense_uniform((n,), 5, torch.float32, cuda)
+    y = torch.empty(m, device=cuda)
+    info = sb.multiply_inspect(a, x, y)
+    assert info.max_row_len > 2048                             # hubs span several tiles
+    sb.multiply(info, a, x, y)
+    vh, rph, cih, xh = v.cpu().numpy(), rp.cpu().numpy(), ci.cpu().numpy(), x.cpu().numpy()
+    y_ref = oracle.spmv("csr", shape, rph, cih, vh, xh)
+    worst = assert_rows_within_bound(y.cpu().numpy(), y_ref, rph,
+                                     oracle.abs_rowsum(rph, cih, vh, xh), "C4")
+    assert worst <= 1.0
+    hist, mx = oracle.rowlen_hist(rph)
+    assert np.array_equal(info.rowlen_hist, hist) and info.max_row_len == mx
+    assert np.array_equal(info.tile_starts, oracle.merge_partition(rph, info.tile_items))
+    # linearity: A(2x + x) == 3 A x up to the same bound
+    y3 = torch.empty(m, device=cuda)
+    sb.multiply(info, a, 3 * x, y3)
+    assert_rows_within_bound(y3.cpu().numpy(), 3 * y_ref, rph,
+                             3 * oracle.abs_rowsum(rph, cih, vh, xh), "C4 linear")
+
+
+def test_csc_spmv(cuda, oracle):
+    """csc_view SpMV (column-major storage): golden fixtures and a random case; the
+    inspect phase builds the row-major image bit-exactly as the oracle does."""
+    for dims in DIMS:
+        g = golden(*dims)
+        m, n, _ = dims
+        v, cp, ri = g["csc_values"], g["csc_ptr"], g["csc_ind"]
+        a = csc_on_device(v, cp, ri, (m, n))
+        x = np.ones(n, np.float32)
+        y = gpu_spmv(a, x, m, np.float32)
+        assert oracle.expect_eq_tolerance(g["csc_spmv"], y).all()
+        xd, yd = dev(x), torch.empty(m, device="cuda")
+        info = sb.multiply_inspect(a, xd, yd)
+        t_rp, t_ci, perm = oracle.csc_row_major_image((m, n), cp, ri)
+        g_rp, g_ci, g_perm = info.effective_csr(np.int32, np.int32)
+        assert np.array_equal(g_rp, t_rp) and np.array_equal(g_ci, t_ci)
+        assert np.array_equal(g_perm, perm)
+        # same addition order as the reference's column scatter -> compare tightly
+        sb.multiply(info, sb.scaled(5, a), xd, yd)
+        assert oracle.expect_eq_tolerance(g["csc_spmv_ascaled_5"], yd.cpu().numpy()).all()

@@ -1,0 +1,205 @@
+"""Pins the oracle (oracle/spblas_oracle.c): against the real reference compiled from
+/root/reference (oracle/_ref, when present), against the committed golden vectors the real
+reference produced, and with the reference tests' own known-answer loops and tolerance
+(test/gtest/spmv_test.cpp:21-34, spmm_test.cpp:26-41, util.hpp:7-23).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import DIMS, GOLDEN, golden
+
+ALPHAS = [-10, 1, 5]
+
+
+def _known_answer_spmv(m, rowptr, colind, values, x, alpha=1):
+    # the triple loop of test/gtest/spmv_test.cpp:21-30
+    ref = np.zeros(m, dtype=values.dtype)
+    for i in range(m):
+        for p in range(rowptr[i], rowptr[i + 1]):
+            ref[i] += values.dtype.type(alpha) * values[p] * x[colind[p]]
+    return ref
+
+
+@pytest.mark.parametrize("dims", DIMS)
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+def test_spmv_matches_golden_bit_exact(oracle, dims, fmt):
+    g = golden(*dims)
+    m, n, _ = dims
+    v, ptr, ind = g[f"{fmt}_values"], g[f"{fmt}_ptr"], g[f"{fmt}_ind"]
+    x = np.ones(n, np.float32)
+    assert np.array_equal(oracle.spmv(fmt, (m, n), ptr, ind, v, x), g[f"{fmt}_spmv"])
+    for a in ALPHAS:
+        assert np.array_equal(oracle.spmv(fmt, (m, n), ptr, ind, v, x, alpha_a=a),
+                              g[f"{fmt}_spmv_ascaled_{a}"])
+        assert np.array_equal(oracle.spmv(fmt, (m, n), ptr, ind, v, x, alpha_x=a),
+                              g[f"{fmt}_spmv_bscaled_{a}"])
+
+
+@pytest.mark.parametrize("dims", DIMS)
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+@pytest.mark.parametrize("k", [1, 8, 32, 64, 512])
+def test_spmm_matches_golden_bit_exact(oracle, dims, fmt, k):
+    g = golden(*dims)
+    m, n, _ = dims
+    v, ptr, ind = g[f"{fmt}_values"], g[f"{fmt}_ptr"], g[f"{fmt}_ind"]
+    B = g[f"dense_B_{k}"]
+    assert np.array_equal(oracle.spmm(fmt, (m, n), ptr, ind, v, B), g[f"{fmt}_spmm_{k}"])
+    if k <= 64:
+        assert np.array_equal(oracle.spmm(fmt, (m, n), ptr, ind, v, B, alpha_a=2.0),
+                              g[f"{fmt}_spmm_ascaled_{k}"])
+
+
+@pytest.mark.parametrize("dims", DIMS)
+def test_reference_known_answer_loop(oracle, dims):
+    """The reference's own acceptance test re-hosted: triple loop + EXPECT_EQ_."""
+    g = golden(*dims)
+    m, n, _ = dims
+    v, rp, ci = g["csr_values"], g["csr_ptr"], g["csr_ind"]
+    x = np.ones(n, np.float32)
+    for alpha in [1] + ALPHAS:
+        y = oracle.spmv("csr", (m, n), rp, ci, v, x, alpha_a=None if alpha == 1 else alpha)
+        ka = _known_answer_spmv(m, rp, ci, v, x, alpha)
+        assert oracle.expect_eq_tolerance(ka, y).all()
+
+
+def test_probe_semantics(oracle):
+    """SURVEY Appendix A probe: duplicates accumulate, empty rows give 0, stale NaN in y is
+    discarded (oracle.spmv pre-fills y with NaN), unreferenced Inf does not propagate."""
+    p = np.load(f"{GOLDEN}/probe_3x4.npz")
+    rp, ci, v, x = p["rowptr"], p["colind"], p["values"], p["x"]
+    assert oracle.spmv("csr", (3, 4), rp, ci, v, x).tolist() == [140.0, 0.0, 160.0]
+    xinf = x.copy()
+    xinf[1] = np.inf
+    assert np.array_equal(oracle.spmv("csr", (3, 4), rp, ci, v, xinf), p["y_inf"])
+    assert np.array_equal(oracle.spmv("csr", (3, 4), rp, ci, v, x, alpha_a=2, alpha_x=3),
+                          p["y_scaled"])
+    assert np.array_equal(oracle.spmv("csc", (4, 3), rp, ci, v, np.ones(3, np.float32)),
+                          p["yt"])
+    assert np.array_equal(oracle.spmv("csr", (3, 4), rp, ci, v.astype(np.int32),
+                                      x.astype(np.int32)), p["y_s32"])
+
+
+def test_against_real_reference_when_present(oracle):
+    """Bit-exact against the real spblas::multiply for every type combination the shim
+    instantiates, including the inspect + multiply(info, ...) spelling."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(7)
+    for (vt, it, ot) in [(np.float32, np.int32, np.int32), (np.float32, np.int32, np.int64),
+                         (np.float64, np.int32, np.int32), (np.float64, np.int32, np.int64),
+                         (np.int32, np.int32, np.int32), (np.float32, np.int64, np.int64)]:
+        m, n = 257, 131
+        lens = rng.integers(0, 40, size=m)
+        lens[5] = 0
+        lens[17] = 300
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(ot)
+        ci = rng.integers(0, n, size=int(rp[-1])).astype(it)
+        if vt == np.int32:
+            v = rng.integers(-9, 9, size=len(ci)).astype(vt)
+            x = rng.integers(-9, 9, size=n).astype(vt)
+            B = rng.integers(-9, 9, size=(n, 9)).astype(vt)
+            aa, ax = 3, -2
+        else:
+            v = rng.standard_normal(len(ci)).astype(vt)
+            x = rng.standard_normal(n).astype(vt)
+            B = rng.standard_normal((n, 9)).astype(vt)
+            aa, ax = 1.5, -0.25
+        for insp in (False, True):
+            for kw in ({}, {"alpha_a": aa}, {"alpha_x": ax}, {"alpha_a": aa, "alpha_x": ax}):
+                a = oracle.spmv("csr", (m, n), rp, ci, v, x, **kw)
+                b = oracle.spmv("csr", (m, n), rp, ci, v, x, impl="reference", inspect=insp, **kw)
+                assert np.array_equal(a, b), (vt, it, ot, kw)
+        # CSC: the same arrays read as the transpose (n x m matrix... here m x n with
+        # colptr over m "columns"): shape (n, m)
+        xt = (rng.standard_normal(m).astype(vt) if vt != np.int32
+              else rng.integers(-9, 9, size=m).astype(vt))
+        a = oracle.spmv("csc", (n, m), rp, ci, v, xt)
+        b = oracle.spmv("csc", (n, m), rp, ci, v, xt, impl="reference")
+        assert np.array_equal(a, b)
+        for kw in ({}, {"alpha_a": aa}, {"alpha_b": ax}):
+            a = oracle.spmm("csr", (m, n), rp, ci, v, B, **kw)
+            b = oracle.spmm("csr", (m, n), rp, ci, v, B, impl="reference", **kw)
+            assert np.array_equal(a, b), (vt, kw)
+        Bt = (rng.standard_normal((m, 5)).astype(vt) if vt != np.int32
+              else rng.integers(-9, 9, size=(m, 5)).astype(vt))
+        a = oracle.spmm("csc", (n, m), rp, ci, v, Bt)
+        b = oracle.spmm("csc", (n, m), rp, ci, v, Bt, impl="reference")
+        assert np.array_equal(a, b)
+
+
+def test_reference_fixtures_match_golden(oracle):
+    """generate_csr through the shim reproduces the committed fixture arrays."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    for (m, n, nnz) in DIMS:
+        g = golden(m, n, nnz)
+        v, rp, ci = oracle.ref_generate_csr(m, n, nnz)
+        assert np.array_equal(v, g["csr_values"])
+        assert np.array_equal(rp, g["csr_ptr"])
+        assert np.array_equal(ci, g["csr_ind"])
+
+
+# ---- inspect-phase restatements -------------------------------------------------------
+def _random_rowptr(rng, rows, kind):
+    if kind == "uniform":
+        lens = rng.integers(0, 12, size=rows)
+    elif kind == "empty":
+        lens = np.zeros(rows, dtype=np.int64)
+    elif kind == "hub":
+        lens = rng.integers(0, 4, size=rows)
+        lens[rows // 3] = 9000
+        lens[rows - 1] = 2500
+    else:
+        lens = np.full(rows, 5)
+    return np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "empty", "hub", "const"])
+@pytest.mark.parametrize("tile", [7, 64, 2048])
+def test_merge_partition_properties(oracle, kind, tile):
+    rng = np.random.default_rng(3)
+    rp = _random_rowptr(rng, 1500, kind) + 11          # non-zero base, as a shard has
+    rows, nnz = len(rp) - 1, int(rp[-1] - rp[0])
+    st = oracle.merge_partition(rp, tile)
+    assert st[0].tolist() == [0, 11] and st[-1].tolist() == [rows, 11 + nnz]
+    d = (st[:, 0] + st[:, 1] - 11)
+    want = np.minimum(np.arange(len(st)) * tile, rows + nnz)
+    assert np.array_equal(d, want)                      # every tile starts on its diagonal
+    assert (np.diff(st[:, 0]) >= 0).all() and (np.diff(st[:, 1]) >= 0).all()
+    # merge order: rows before the split are finished, the split row is not over-consumed
+    for r, k in st:
+        if r > 0:
+            assert rp[r] <= k
+        if r < rows:
+            assert k <= rp[r + 1]
+
+
+def test_rowlen_hist_and_segments(oracle):
+    rng = np.random.default_rng(5)
+    rp = _random_rowptr(rng, 4000, "hub")
+    hist, mx = oracle.rowlen_hist(rp)
+    lens = np.diff(rp)
+    assert hist.sum() == len(lens) and mx == lens.max()
+    assert hist[0] == (lens == 0).sum() and hist[1] == (lens == 1).sum()
+    assert hist[2] == ((lens >= 2) & (lens < 4)).sum()
+    assert hist[14] == ((lens >= 8192) & (lens < 16384)).sum() == 1
+    segs = oracle.row_segments(rp, 4096)
+    assert segs[:, 0].tolist() == [4000 // 3] * 3
+    assert segs[0, 1] == rp[4000 // 3] and segs[-1, 2] == rp[4000 // 3 + 1]
+    assert (segs[:, 2] - segs[:, 1]).tolist() == [4096, 4096, 9000 - 8192]
+    assert oracle.rowlen_hist(np.array([0, 5, 3]))[1] == -1     # not monotone
+
+
+def test_csc_row_major_image(oracle):
+    g = golden(100, 1000, 10000)
+    cp, ri, v = g["csc_ptr"], g["csc_ind"], g["csc_values"]
+    t_rp, t_ci, perm = oracle.csc_row_major_image((100, 1000), cp, ri)
+    assert t_rp[-1] == len(ri)
+    # the image is the same matrix: CSR product on the image == CSC product
+    x = np.arange(1000, dtype=np.float32) % 7
+    y_csc = oracle.spmv("csc", (100, 1000), cp, ri, v, x)
+    y_img = oracle.spmv("csr", (100, 1000), t_rp.astype(np.int32), t_ci.astype(np.int32),
+                        v[perm], x)
+    assert np.array_equal(y_csc, y_img)                 # same order of additions: bit-exact
+    for i in range(100):
+        seg = perm[t_rp[i]:t_rp[i + 1]]
+        assert (np.diff(seg) > 0).all()                 # stable: storage order kept
