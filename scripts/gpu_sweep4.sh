@@ -1,0 +1,20 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+run() { name=$1; shift
+  env "$@" timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-e2e 2>gpurun_out/sweep_$name.err | python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: continue
+    print('$name', 'ms=%.4f'%d['ms_per_step'], 'kern_ms=%.4f'%d['roofline']['kernel_ms'], 'GB/s=%.0f'%d['roofline']['achieved'], 'frac=%.3f'%d['roofline']['frac'])
+" | tee -a gpurun_out/sweep.txt
+}
+: > gpurun_out/sweep.txt
+run v1_default SPBLAS_B200_SPMV_VARIANT=1
+for cfg in "8 2 1024 3" "8 2 1024 4" "8 2 1024 5" "8 1 2048 4" "8 1 2048 5" "8 1 4096 3" "16 1 1024 4" "16 1 1024 8" "16 1 2048 3" "16 1 2048 4" "16 1 2048 5" "16 1 4096 2" "8 3 1024 3" "8 3 512 4" "8 2 512 6"; do
+  set -- $cfg
+  run v1_w$1_c$2_t$3_s$4 SPBLAS_B200_CONSUMER_WARPS=$1 SPBLAS_B200_CTAS_PER_SM=$2 SPBLAS_B200_TILE_ITEMS=$3 SPBLAS_B200_STAGES=$4
+done

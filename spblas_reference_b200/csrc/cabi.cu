@@ -61,7 +61,7 @@ namespace {
 void release_all(spblas_b200_plan* p) {
   DeviceBuffer* bufs[] = {&p->own_rowptr,  &p->own_colind, &p->own_perm,
                           &p->sort_tmp0,   &p->sort_tmp1,  &p->sort_tmp2,
-                          &p->sort_ws,     &p->tile_starts, &p->carry_row,
+                          &p->sort_ws,     &p->tile_starts, &p->tile_uniform, &p->carry_row,
                           &p->carry_val,   &p->segments,   &p->seg_partial,
                           &p->seg_counter, &p->stats};
   for (DeviceBuffer* b : bufs)
@@ -138,6 +138,19 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
   p->num_sms = sms > 0 ? sms : 148;
   if (const char* v = std::getenv("SPBLAS_B200_SPMV_VARIANT"))
     p->forced_variant = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_TILE_ITEMS")) {
+    const int t = std::atoi(v);
+    if (t >= 256 && t <= kSpmvMaxTileItems && t % 4 == 0)
+      p->tile_items_override = t;
+  }
+  if (const char* v = std::getenv("SPBLAS_B200_STAGES"))
+    p->stages = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_CTAS_PER_SM"))
+    p->ctas_per_sm = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_CONSUMER_WARPS"))
+    p->consumer_warps = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_DEBUG_MODE"))
+    p->debug_mode = std::atoi(v);
   *out = p;
   return SPBLAS_B200_SUCCESS;
 }

@@ -120,6 +120,33 @@ merge_partition_kernel(const O* __restrict__ rowptr, int64_t rows, int64_t nnz,
   tile_starts[2 * t + 1] = base + (d - lo);
 }
 
+// Per tile: do all complete rows after the first (rows row0+1 .. row1-1, whose ends
+// lie in the tile) have the same length L, 1 <= L <= 8?  Then out[t] = L, else 0.
+// One warp per tile.  Stencil-like and fixed-degree matrices are uniform almost
+// everywhere; the execute kernel then needs no row-end lookups for the tile.
+template <typename O>
+__global__ void __launch_bounds__(256)
+tile_uniform_kernel(const O* __restrict__ rowptr,
+                    const int64_t* __restrict__ tile_starts, int64_t num_tiles,
+                    int max_len, int* __restrict__ out) {
+  const int64_t t = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= num_tiles)
+    return;
+  const int64_t row0 = tile_starts[2 * t], row1 = tile_starts[2 * t + 2];
+  int64_t L = -1;
+  if (row1 - row0 >= 2)
+    L = int64_t(rowptr[row0 + 2]) - int64_t(rowptr[row0 + 1]);
+  bool ok = L >= 1 && L <= max_len;
+  if (ok) {
+    for (int64_t r = row0 + 1 + lane; r < row1; r += 32)
+      ok = ok && (int64_t(rowptr[r + 1]) - int64_t(rowptr[r]) == L);
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0)
+    out[t] = ok ? int(L) : 0;
+}
+
 // ---------------------------------------------------------------------------
 // 3. CSC -> row-major image
 // ---------------------------------------------------------------------------
@@ -247,7 +274,10 @@ int inspect_rows(spblas_b200_plan* p, const O* rowptr, int64_t rows, int flags) 
   }
 
   // merge-path partition table
-  p->tile_items = kSpmvTileItems;
+  if (p->tile_items_override > 0)
+    p->tile_items = p->tile_items_override;
+  else
+    p->tile_items = kSpmvTileItems;
   const int64_t total = rows + p->nnz;
   p->num_tiles = (total + p->tile_items - 1) / p->tile_items;
   rc = reserve(p, p->tile_starts, size_t(p->num_tiles + 1) * 2 * sizeof(int64_t));
@@ -266,6 +296,18 @@ int inspect_rows(spblas_b200_plan* p, const O* rowptr, int64_t rows, int flags) 
         rowptr, rows, p->nnz, p->base, p->tile_items, p->num_tiles,
         static_cast<int64_t*>(p->tile_starts.p));
     if (int e = launch_ok(p, "merge_partition_kernel"))
+      return e;
+  }
+  rc = reserve(p, p->tile_uniform, size_t(p->num_tiles + 1) * sizeof(int));
+  if (rc)
+    return rc;
+  if (p->num_tiles > 0) {
+    const int64_t nthreads = p->num_tiles * 32;
+    const int grid = int((nthreads + 255) / 256);
+    tile_uniform_kernel<O><<<grid, 256, 0, s>>>(
+        rowptr, static_cast<const int64_t*>(p->tile_starts.p), p->num_tiles, 8,
+        static_cast<int*>(p->tile_uniform.p));
+    if (int e = launch_ok(p, "tile_uniform_kernel"))
       return e;
   }
 

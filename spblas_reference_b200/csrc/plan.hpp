@@ -24,10 +24,20 @@ constexpr int kSpmvTileItems = 2048;
 // SpMM: rows longer than this are cut into segments of this many nonzeros
 constexpr int64_t kSpmmSegment = 4096;
 
+// largest tile the kernels' shared-memory carve-up is sized for
+constexpr int kSpmvMaxTileItems = 4096;
+
 // SpMV kernel variants (reported by SPBLAS_B200_Q_SPMV_VARIANT)
 enum SpmvVariant : int {
   kVariantAuto = -1,
-  kVariantMergeTile = 0, // merge-path tiles, smem-staged products, adaptive row reduce
+  // one tile per CTA, register-staged loads, products through shared memory.
+  // Handles any pointer alignment; the fallback when colind/values are not
+  // 16-byte aligned.
+  kVariantMergeTile = 0,
+  // persistent CTAs, TMA bulk copies of colind/values (cp.async.bulk + mbarrier)
+  // and cp.async of the row ends into a multi-stage shared-memory ring, one
+  // producer warp + 8 consumer warps that reduce rows straight out of the ring.
+  kVariantPipelined = 1,
 };
 
 struct DeviceBuffer {
@@ -65,8 +75,14 @@ struct spblas_b200_plan {
 
   // ---- merge-path partition --------------------------------------------------
   int tile_items = b200::kSpmvTileItems;
+  int tile_items_override = 0; // env SPBLAS_B200_TILE_ITEMS (tuning)
+  int stages = 0;              // env SPBLAS_B200_STAGES (0 = default)
+  int ctas_per_sm = 0;         // env SPBLAS_B200_CTAS_PER_SM (0 = default)
+  int consumer_warps = 0;      // env SPBLAS_B200_CONSUMER_WARPS (8 or 16; 0 = default)
+  int debug_mode = 0;          // env SPBLAS_B200_DEBUG_MODE (1: stream only, 2: no copies) — wrong results
   int64_t num_tiles = 0;
   b200::DeviceBuffer tile_starts; // int64 (row, nnz) pairs, num_tiles + 1 entries
+  b200::DeviceBuffer tile_uniform; // int32 per tile: common length of the tile's complete rows (0: mixed)
   b200::DeviceBuffer carry_row;   // int64 per tile
   b200::DeviceBuffer carry_val;   // 8 bytes per tile
 

@@ -5,21 +5,36 @@
 //  y[i] += a_ik * x[k] in storage order) and the cusparseSpMV call of the
 // reference's NVIDIA backend (include/spblas/vendor/cusparse/spmv_impl.hpp:80-84).
 //
-// Kernel: merge-path tiles.  The inspect phase cut the merged sequence
-// (row ends ++ nonzeros) into tiles of kSpmvTileItems items; one CTA owns one
-// tile, so every CTA streams the same number of bytes whatever the row-length
-// distribution (uniform 5-point stencil rows, Poisson(10) rows, R-MAT hubs).
-//   phase 1  row-end offsets of the tile -> shared memory (coalesced)
-//   phase 2  colind/values streamed with 128-bit no-L1-allocate loads, x gathered
-//            through the read-only path, products -> shared memory
-//   phase 3  per-row reduction out of shared memory: thread-per-row for short
-//            rows (long rows of such a tile are deferred to a warp-per-row
-//            worklist), warp-per-row with a shuffle reduction for long-row tiles
-//   phase 4  the tile's trailing partial row becomes a carry (row, value); a
-//            second tiny kernel adds carries to y in tile order (deterministic,
-//            no floating-point atomics).
-// y is written exactly once per row by the tile that holds the row's end, so
-// beta = 0 semantics (stale y, even NaN, is discarded) hold without a memset.
+// Work decomposition: merge-path tiles.  The inspect phase cut the merged
+// sequence (row ends ++ nonzeros) into tiles of tile_items items, so every tile
+// streams the same number of bytes whatever the row-length distribution (uniform
+// 5-point stencil rows, Poisson(10) rows, R-MAT hubs).  A tile's nonzero range
+// [k0, k1) starts anywhere; the kernels fetch the 16-byte aligned superset
+// [k0 & ~3, ceil4(k1)) (at most 6 extra elements per tile) and index shared memory
+// from the aligned origin, so all bulk traffic is 128-bit aligned.
+//
+// Two kernels consume that partition:
+//
+//  spmv_pipe_kernel (default) — persistent CTAs, each owning a contiguous run of
+//    tiles.  One producer warp runs ahead of eight consumer warps through a ring of
+//    shared-memory stages: per tile it issues two TMA bulk copies
+//    (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) for the
+//    colind and values ranges and element-wise cp.async for the row-end offsets
+//    (any alignment), all tracked by the stage's "full" mbarrier.  Consumers wait
+//    on the barrier, reduce complete rows straight out of the stage (thread-per-row
+//    for short rows, in storage order like the reference; warp-per-row with a
+//    shuffle reduction for long rows), gather x through the read-only path, write y
+//    once, and release the stage through its "empty" mbarrier.  HBM latency is
+//    hidden by the (stages-1) tiles in flight per CTA instead of by occupancy.
+//
+//  spmv_merge_tile_kernel (fallback; also selectable for A/B runs) — one tile per
+//    CTA, register-staged 128-bit loads, products through shared memory.  Handles
+//    colind/values that are not 16-byte aligned.
+//
+// In both, the tile's trailing partial row becomes a carry (row, value); a second
+// tiny kernel adds carries to y in tile order (deterministic, no floating-point
+// atomics).  y is written exactly once per row by the tile that holds the row's
+// end, so beta = 0 semantics (stale y, even NaN, is discarded) hold without a memset.
 #include "device_utils.cuh"
 #include "plan.hpp"
 
@@ -33,7 +48,571 @@ struct alignas(16) Vec4 {
 };
 
 constexpr int kLongRow = 64; // thread-per-row tiles hand rows longer than this to warps
+constexpr int kTileSlack = 16; // a tile can exceed tile_items by < 8 nonzeros
 
+// ============================================================================
+// mbarrier / TMA bulk-copy / cp.async primitives (PTX; sm_90+ features used on
+// sm_100a).  Shared addresses are 32-bit shared-window addresses.
+// ============================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+               "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar`.
+// src, dst and bytes are multiples of 16.  The data is streamed once: L2 evict_first.
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src,
+                                            uint32_t bytes, uint32_t bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(uint32_t dst, const void* src) {
+  static_assert(BYTES == 4 || BYTES == 8, "element-wise cp.async of 4 or 8 bytes");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src),
+               "n"(BYTES)
+               : "memory");
+}
+
+// arrive on `bar` once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ============================================================================
+// Pipelined kernel
+// ============================================================================
+constexpr int kPipeHeaderBytes = 64;
+constexpr int kPipeMaxStages = 8;
+constexpr int kMaxUniformLen = 8; // longest row length with an unrolled exact path
+
+struct PipeHeader {
+  long long row0; // first row whose end lies in this tile
+  long long kq0;  // absolute nonzero index of local slot 0 (k0 rounded down to 4)
+  int nr;         // row ends in this tile
+  int lo;         // local index of the tile's first nonzero (k0 - kq0)
+  int hi;         // local index one past the tile's last nonzero (k1 - kq0)
+  int nslots;     // local slots held by the stage (multiple of 4)
+  int off_b;      // byte offset of the second staged array (values, or perm)
+  int off_prod;   // byte offset of the products (== off_b unless a CSC image)
+  int off_rowend; // byte offset of the row ends
+  int uniform;    // L if rows row0+1 .. row0+nr-1 all have L entries (1..8), else 0
+};
+static_assert(sizeof(PipeHeader) <= kPipeHeaderBytes, "header too large");
+
+// bytes one stage's data area must hold for a tile of `tile_items`: per nonzero
+// colind + values (products overwrite the values in place); a CSC image stages
+// colind + permutation and needs separate room for the products; a row end costs one
+// offset.  Whichever is larger per merge item bounds the tile.
+__host__ __device__ inline int pipe_stage_data_bytes(int tile_items, int sT, int sI,
+                                                     int sO, bool perm) {
+  const int per_nz = perm ? sI + sO + sT : sI + sT;
+  const int per_item = per_nz > sO ? per_nz : sO;
+  const int bytes = per_item * (tile_items + kTileSlack) + 128;
+  return (bytes + 127) & ~127;
+}
+
+// ---- path 1: uniform tiles (stencils, fixed-degree graphs) ----------------------
+// The inspect phase found that every complete row of the tile after the first has
+// exactly L entries, so row r of those starts at e0 + L*r: no row-end lookups, no
+// per-row branches.  One thread per row; all L column indices are read, all L
+// gathers of x issued, then the FMAs run in storage order (the reference's order).
+// The 32 lanes of a warp own 32 consecutive rows, so gather j of every lane falls in
+// the same few 128-byte lines of x for a banded matrix: the gathers are coalesced.
+template <int L, typename T, typename I>
+__device__ __forceinline__ T dot_exact(const I* __restrict__ col,
+                                       const T* __restrict__ val,
+                                       const T* __restrict__ x, int b) {
+  I c[L];
+  T xv[L], av[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j)
+    c[j] = col[b + j];
+#pragma unroll
+  for (int j = 0; j < L; ++j)
+    xv[j] = ld_ro(x + c[j]);
+#pragma unroll
+  for (int j = 0; j < L; ++j)
+    av[j] = val[b + j];
+  T sum = av[0] * xv[0];
+#pragma unroll
+  for (int j = 1; j < L; ++j)
+    sum += av[j] * xv[j];
+  return sum;
+}
+
+template <int L, int CONS, typename T, typename I>
+__device__ __forceinline__ void
+uniform_rows(const I* __restrict__ col, const T* __restrict__ val,
+             const T* __restrict__ x, T* __restrict__ yrow, const T alpha, int e0,
+             int nrows, int tid) {
+  for (int r = tid; r < nrows; r += CONS)
+    yrow[r] = alpha * dot_exact<L, T, I>(col, val, x, e0 + L * r);
+}
+
+// a row (or row fragment) [b, e) by one warp, straight from the staged operands
+template <typename T, typename I>
+__device__ __forceinline__ T dot_warp(const I* __restrict__ col,
+                                      const T* __restrict__ val,
+                                      const T* __restrict__ x, int b, int e, int lane) {
+  T sum = T(0);
+  int i = b + lane;
+  for (; i + 32 < e; i += 64) {
+    const I c0 = col[i], c1 = col[i + 32];
+    const T x0 = ld_ro(x + c0), x1 = ld_ro(x + c1);
+    sum += val[i] * x0;
+    sum += val[i + 32] * x1;
+  }
+  if (i < e)
+    sum += val[i] * ld_ro(x + col[i]);
+  return warp_reduce_sum(sum);
+}
+
+// ---- path 2: general tiles -------------------------------------------------------
+// (A) flat product phase: every consumer thread turns whole QUADS of staged entries
+// into products a_ik * x_k with no knowledge of rows: two quads per thread are
+// fetched from shared memory with 128-bit loads, their eight gathers of x are issued
+// together through the read-only path, and the products are written back with
+// 128-bit stores.  There are no per-element predicates: every slot of the stage holds
+// a real matrix entry (entries of the neighbouring tiles in the aligned fringe; the
+// producer zero-fills slots past the end of the arrays), and products outside
+// [lo, hi) are simply never read.  (B) after a consumer-only barrier, rows are summed
+// out of shared memory.
+template <typename T, typename I>
+__device__ __forceinline__ void quad_products(const I* __restrict__ col, const T* val,
+                                              T* prod, const T* __restrict__ x, int qa,
+                                              int qb, bool two) {
+  const Vec4<I> ca = *reinterpret_cast<const Vec4<I>*>(col + 4 * qa);
+  const Vec4<T> va = *reinterpret_cast<const Vec4<T>*>(val + 4 * qa);
+  Vec4<I> cb = ca;
+  Vec4<T> vb = va;
+  if (two) {
+    cb = *reinterpret_cast<const Vec4<I>*>(col + 4 * qb);
+    vb = *reinterpret_cast<const Vec4<T>*>(val + 4 * qb);
+  }
+  T xa[4], xb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    xa[j] = ld_ro(x + ca.v[j]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    xb[j] = ld_ro(x + cb.v[j]);
+  Vec4<T> pa, pb;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    pa.v[j] = va.v[j] * xa[j];
+    pb.v[j] = vb.v[j] * xb[j];
+  }
+  *reinterpret_cast<Vec4<T>*>(prod + 4 * qa) = pa;
+  if (two)
+    *reinterpret_cast<Vec4<T>*>(prod + 4 * qb) = pb;
+}
+
+// CSC image: the stage holds the value permutation, the value itself is gathered
+template <typename T, typename I, typename O>
+__device__ __forceinline__ void quad_products_perm(const I* __restrict__ col,
+                                                   const O* __restrict__ perm,
+                                                   T* __restrict__ prod,
+                                                   const T* __restrict__ values,
+                                                   const T* __restrict__ x, int q) {
+  const Vec4<I> c = *reinterpret_cast<const Vec4<I>*>(col + 4 * q);
+  const Vec4<O> pi = *reinterpret_cast<const Vec4<O>*>(perm + 4 * q);
+  T a[4], xv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    a[j] = ld_ro(values + pi.v[j]);
+    xv[j] = ld_ro(x + c.v[j]);
+  }
+  Vec4<T> p;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    p.v[j] = a[j] * xv[j];
+  *reinterpret_cast<Vec4<T>*>(prod + 4 * q) = p;
+}
+
+template <typename T>
+__device__ __forceinline__ T prod_sum_thread(const T* __restrict__ prod, int b, int e) {
+  T sum = T(0);
+#pragma unroll 1
+  for (int i = b; i < e; ++i) // storage order, like the reference's row loop
+    sum += prod[i];
+  return sum;
+}
+
+template <typename T>
+__device__ __forceinline__ T prod_sum_warp(const T* __restrict__ prod, int b, int e,
+                                           int lane) {
+  T sum = T(0);
+  for (int i = b + lane; i < e; i += 32)
+    sum += prod[i];
+  return warp_reduce_sum(sum);
+}
+
+template <typename T, typename I, typename O, int CW>
+__global__ void __launch_bounds__(CW * 32 + 32, CW <= 8 ? 3 : 1)
+spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
+                 const T* __restrict__ values, const O* __restrict__ perm,
+                 const T* __restrict__ x, T* __restrict__ y, const T alpha,
+                 const int64_t* __restrict__ tile_starts,
+                 const int* __restrict__ tile_uniform, const int64_t num_tiles,
+                 const int64_t rows, const int64_t nnz_end,
+                 int64_t* __restrict__ carry_row, T* __restrict__ carry_val,
+                 const int stages, const int stage_data_bytes, const int debug_mode) {
+  constexpr int kPipeConsumerWarps = CW;        // consumer warps; warp CW is the producer
+  constexpr int kPipeConsumers = CW * 32;
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: [full barriers][empty barriers][pad to 128][stage 0 header+data]...
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const int stage_bytes = kPipeHeaderBytes + stage_data_bytes;
+  unsigned char* stage_base = smem + 128;
+  __shared__ T s_red[kPipeConsumerWarps];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const bool has_perm = perm != nullptr;
+
+  // contiguous run of tiles for this CTA
+  const int64_t t_begin = num_tiles * int64_t(blockIdx.x) / gridDim.x;
+  const int64_t t_end = num_tiles * int64_t(blockIdx.x + 1) / gridDim.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&bars[s]), 32 + 1);                 // full: 32 cp.async arrivals + expect_tx
+      mbar_init(smem_u32(&bars[kPipeMaxStages + s]), kPipeConsumerWarps); // empty
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kPipeConsumerWarps) {
+    // ======================= producer warp ======================================
+    const uint64_t policy = policy_evict_first();
+    int s = 0;
+    uint32_t phase = 0;
+    // tile coordinates are prefetched one tile ahead so that the table's load
+    // latency never sits between two tiles' copies
+    int64_t cur_row = 0, cur_k = 0, nxt_row = 0, nxt_k = 0;
+    int cur_uni = 0, nxt_uni = 0;
+    if (t_begin < t_end) {
+      cur_row = tile_starts[2 * t_begin];
+      cur_k = tile_starts[2 * t_begin + 1];
+      nxt_row = tile_starts[2 * t_begin + 2];
+      nxt_k = tile_starts[2 * t_begin + 3];
+      cur_uni = has_perm ? 0 : tile_uniform[t_begin];
+    }
+    for (int64_t t = t_begin; t < t_end; ++t) {
+      const int64_t row0 = cur_row, k0 = cur_k, row1 = nxt_row, k1 = nxt_k;
+      const int uni = cur_uni;
+      cur_row = nxt_row;
+      cur_k = nxt_k;
+      if (t + 1 < t_end) {
+        nxt_row = tile_starts[2 * t + 4];
+        nxt_k = tile_starts[2 * t + 5];
+        nxt_uni = has_perm ? 0 : tile_uniform[t + 1];
+      }
+      cur_uni = nxt_uni;
+      const int nr = int(row1 - row0);
+      const int64_t kq0 = k0 & ~int64_t(3);             // aligned origin of the stage
+      const int nslots = int(((k1 - kq0) + 3) & ~int64_t(3)); // local slots (multiple of 4)
+      const int b_elem = has_perm ? int(sizeof(O)) : int(sizeof(T));
+      const int off_b = nslots * int(sizeof(I));
+      const int off_prod = has_perm ? off_b + nslots * int(sizeof(O)) : off_b;
+      const int off_rowend = (off_prod + nslots * int(sizeof(T)) + 15) & ~15;
+      // quads that lie entirely inside the arrays are bulk-copied; the arrays' last
+      // partial quad (if any) is copied element-wise below
+      const int64_t kfull = nnz_end & ~int64_t(3);
+      int64_t kb1 = kq0 + nslots;
+      if (kb1 > kfull)
+        kb1 = kfull;
+      const int bulk = kb1 > kq0 ? int(kb1 - kq0) : 0;
+
+      unsigned char* st = stage_base + size_t(s) * stage_bytes;
+      unsigned char* data = st + kPipeHeaderBytes;
+      const uint32_t full = smem_u32(&bars[s]);
+      const uint32_t empty = smem_u32(&bars[kPipeMaxStages + s]);
+
+      if (lane == 0)
+        mbar_wait(empty, phase ^ 1u); // stage free (passes at once on the first lap)
+      __syncwarp();
+
+      // Slots past the end of the arrays (last tile only) get column 0 and a zero
+      // value / permutation 0, so that the predicate-free product phase gathers valid
+      // addresses.  Plain stores: they must precede lane 0's releasing arrive below.
+      const bool ragged_end = kq0 + nslots > kfull;
+      if (ragged_end) {
+        for (int li = bulk + lane; li < nslots; li += 32) {
+          if (kq0 + li >= nnz_end) {
+            reinterpret_cast<I*>(data)[li] = I(0);
+            if (has_perm)
+              reinterpret_cast<O*>(data + off_b)[li] = O(0);
+            else
+              reinterpret_cast<T*>(data + off_b)[li] = T(0);
+          }
+        }
+        __syncwarp();
+      }
+
+      if (lane == 0) {
+        PipeHeader* h = reinterpret_cast<PipeHeader*>(st);
+        h->row0 = row0;
+        h->kq0 = kq0;
+        h->nr = nr;
+        h->lo = int(k0 - kq0);
+        h->hi = int(k1 - kq0);
+        h->nslots = nslots;
+        h->off_b = off_b;
+        h->off_prod = off_prod;
+        h->off_rowend = off_rowend;
+        h->uniform = uni;
+        mbar_arrive_expect_tx(full, uint32_t(bulk) * uint32_t(int(sizeof(I)) + b_elem));
+        if (bulk > 0) {
+          tma_load_1d(smem_u32(data), colind + kq0, uint32_t(bulk) * sizeof(I), full,
+                      policy);
+          if (!has_perm)
+            tma_load_1d(smem_u32(data + off_b), values + kq0, uint32_t(bulk) * sizeof(T),
+                        full, policy);
+          else
+            tma_load_1d(smem_u32(data + off_b), perm + kq0, uint32_t(bulk) * sizeof(O),
+                        full, policy);
+        }
+      }
+      // row ends: element-wise async copies (no alignment requirement).  A uniform
+      // tile only needs the first one.
+      {
+        const uint32_t dst0 = smem_u32(data + off_rowend);
+        const O* src0 = rowptr + row0 + 1;
+        const int ncopy = uni > 0 ? (nr > 0 ? 1 : 0) : nr;
+        for (int q = lane; q < ncopy; q += 32)
+          cp_async_small<sizeof(O)>(dst0 + q * uint32_t(sizeof(O)), src0 + q);
+      }
+      // the arrays' last partial quad (last tile only): real entries element-wise
+      if (ragged_end) {
+        for (int li = bulk + lane; li < nslots; li += 32) {
+          const int64_t k = kq0 + li;
+          if (k < nnz_end) {
+            cp_async_small<sizeof(I)>(smem_u32(data) + uint32_t(li) * sizeof(I), colind + k);
+            if (!has_perm)
+              cp_async_small<sizeof(T)>(smem_u32(data + off_b) + uint32_t(li) * sizeof(T),
+                                        values + k);
+            else
+              cp_async_small<sizeof(O)>(smem_u32(data + off_b) + uint32_t(li) * sizeof(O),
+                                        perm + k);
+          }
+        }
+      }
+      cp_async_arrive_noinc(full);
+
+      if (++s == stages) {
+        s = 0;
+        phase ^= 1u;
+      }
+    }
+    return;
+  }
+
+  // ========================= consumer warps ========================================
+  int s = 0;
+  uint32_t phase = 0;
+  for (int64_t t = t_begin; t < t_end; ++t) {
+    unsigned char* st = stage_base + size_t(s) * stage_bytes;
+    unsigned char* data = st + kPipeHeaderBytes;
+    mbar_wait(smem_u32(&bars[s]), phase);
+
+    const PipeHeader* hp = reinterpret_cast<const PipeHeader*>(st);
+    const int nr = hp->nr, lo = hp->lo, hi = hp->hi;
+    const int uni = hp->uniform;
+    const int64_t row0 = hp->row0;
+    const O kq0 = O(hp->kq0);
+    const I* col = reinterpret_cast<const I*>(data);
+    T* prod = reinterpret_cast<T*>(data + hp->off_prod);
+    const O* rowend = reinterpret_cast<const O*>(data + hp->off_rowend);
+
+    int tb; // local index where the trailing partial row starts
+    bool tail_from_prod;
+    if (debug_mode == 1) {
+      tb = hi; // tuning aid: stream only
+      tail_from_prod = true;
+    } else if (uni > 0 && nr > 0) {
+      // ---- path 1: uniform tile ----------------------------------------------------
+      const T* val = prod; // !has_perm: values are staged at off_prod == off_b
+      const int e0 = int(rowend[0] - kq0);
+      // first row: its head may lie in the previous tile and it may be long
+      if (warp == 0) {
+        const T sum = dot_warp<T, I>(col, val, x, lo, e0, lane);
+        if (lane == 0)
+          y[row0] = alpha * sum;
+      }
+      T* yrow = y + row0 + 1;
+      const int nrows = nr - 1;
+      switch (uni) {
+      case 1: uniform_rows<1, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
+      case 2: uniform_rows<2, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
+      case 3: uniform_rows<3, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
+      case 4: uniform_rows<4, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
+      case 5: uniform_rows<5, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
+      case 6: uniform_rows<6, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
+      case 7: uniform_rows<7, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
+      default: uniform_rows<8, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
+      }
+      tb = e0 + uni * nrows;
+      tail_from_prod = false;
+    } else {
+      // ---- path 2 (A): flat products -------------------------------------------------
+      const int nq = hp->nslots >> 2;
+      if (!has_perm) {
+        int q = tid;
+        for (; q + kPipeConsumers < nq; q += 2 * kPipeConsumers)
+          quad_products<T, I>(col, prod, prod, x, q, q + kPipeConsumers, true);
+        if (q < nq)
+          quad_products<T, I>(col, prod, prod, x, q, q, false);
+      } else {
+        const O* pst = reinterpret_cast<const O*>(data + hp->off_b);
+        for (int q = tid; q < nq; q += kPipeConsumers)
+          quad_products_perm<T, I, O>(col, pst, prod, values, x, q);
+      }
+      named_barrier_sync(1, kPipeConsumers);
+      // ---- path 2 (B): rows out of shared memory ----------------------------------------
+      const int nzt = hi - lo;
+      if (nr > 0) {
+        if (nzt <= nr * 12) {
+          // short rows: one thread per row.  A row longer than kLongRow inside such
+          // a tile is summed by the whole warp (ballot + broadcast of its bounds).
+          for (int q0 = warp * 32; q0 < nr; q0 += kPipeConsumers) {
+            const int q = q0 + lane;
+            int b = 0, e = 0;
+            if (q < nr) {
+              b = q == 0 ? lo : int(rowend[q - 1] - kq0);
+              e = int(rowend[q] - kq0);
+            }
+            const bool is_long = e - b > kLongRow;
+            if (q < nr && !is_long)
+              y[row0 + q] = alpha * prod_sum_thread(prod, b, e);
+            unsigned todo = __ballot_sync(0xffffffffu, is_long);
+            while (todo) {
+              const int src = __ffs(todo) - 1;
+              todo &= todo - 1;
+              const int bb = __shfl_sync(0xffffffffu, b, src);
+              const int ee = __shfl_sync(0xffffffffu, e, src);
+              const T sum = prod_sum_warp(prod, bb, ee, lane);
+              if (lane == 0)
+                y[row0 + q0 + src] = alpha * sum;
+            }
+          }
+        } else {
+          // long rows: one warp per row
+          for (int q = warp; q < nr; q += kPipeConsumerWarps) {
+            const int b = q == 0 ? lo : int(rowend[q - 1] - kq0);
+            const int e = int(rowend[q] - kq0);
+            const T sum = prod_sum_warp(prod, b, e, lane);
+            if (lane == 0)
+              y[row0 + q] = alpha * sum;
+          }
+        }
+      }
+      tb = nr > 0 ? int(rowend[nr - 1] - kq0) : lo;
+      tail_from_prod = true;
+    }
+
+    // ---- trailing partial row -> carry --------------------------------------------------
+    const int tlen = hi - tb;
+    if (row0 + nr < rows && tlen > 0) {
+      if (!tail_from_prod) {
+        // uniform tile: the fragment is shorter than a row (at most 8 entries)
+        if (warp == 1 % kPipeConsumerWarps) {
+          const T sum = dot_warp<T, I>(col, prod, x, tb, hi, lane);
+          if (lane == 0) {
+            carry_row[t] = row0 + nr;
+            carry_val[t] = sum;
+          }
+        }
+      } else if (tlen <= 256) {
+        if (warp == 0) {
+          const T sum = prod_sum_warp(prod, tb, hi, lane);
+          if (lane == 0) {
+            carry_row[t] = row0 + nr;
+            carry_val[t] = sum;
+          }
+        }
+      } else {
+        T sum = T(0);
+        for (int i = tb + tid; i < hi; i += kPipeConsumers)
+          sum += prod[i];
+        sum = warp_reduce_sum(sum);
+        if (lane == 0)
+          s_red[warp] = sum;
+        named_barrier_sync(2, kPipeConsumers);
+        if (tid == 0) {
+          T tot = T(0);
+#pragma unroll
+          for (int w = 0; w < kPipeConsumerWarps; ++w)
+            tot += s_red[w];
+          carry_row[t] = row0 + nr;
+          carry_val[t] = tot;
+        }
+        named_barrier_sync(2, kPipeConsumers); // s_red reusable
+      }
+    } else if (tid == 0) {
+      carry_row[t] = -1;
+    }
+
+    // release the stage
+    __syncwarp();
+    if (lane == 0)
+      mbar_arrive(smem_u32(&bars[kPipeMaxStages + s]));
+    if (++s == stages) {
+      s = 0;
+      phase ^= 1u;
+    }
+  }
+}
+
+// ============================================================================
+// Fallback kernel: one tile per CTA
+// ============================================================================
 template <typename T, typename I, typename O>
 __global__ void __launch_bounds__(kSpmvThreads)
 spmv_merge_tile_kernel(const O* __restrict__ rowptr,
@@ -42,16 +621,16 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
                        const O* __restrict__ perm, const T* __restrict__ x,
                        T* __restrict__ y, const T alpha,
                        const int64_t* __restrict__ tile_starts,
-                       const int64_t rows, int64_t* __restrict__ carry_row,
+                       const int64_t rows, const int64_t nnz_end,
+                       int64_t* __restrict__ carry_row,
                        T* __restrict__ carry_val, const int vec_ok) {
   constexpr int THREADS = kSpmvThreads;
-  constexpr int TILE = kSpmvTileItems;
-  constexpr int QITER = TILE / 4 / THREADS;
+  constexpr int TILE = kSpmvMaxTileItems;
   constexpr int WARPS = THREADS / 32;
-  constexpr int MAXLONG = TILE / kLongRow + 1;
+  constexpr int MAXLONG = TILE / kLongRow + 2;
 
-  __shared__ __align__(16) T s_prod[TILE + 4];
-  __shared__ int s_rowend[TILE];
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  // s_prod[tile + slack] followed by s_rowend[tile + slack]; sized by the host
   __shared__ T s_red[WARPS];
   __shared__ int s_long[MAXLONG];
   __shared__ int s_nlong;
@@ -63,72 +642,71 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
   const int64_t row0 = tile_starts[2 * t], k0 = tile_starts[2 * t + 1];
   const int64_t row1 = tile_starts[2 * t + 2], k1 = tile_starts[2 * t + 3];
   const int nr = int(row1 - row0);
-  const int64_t k0a = k0 & ~int64_t(3); // origin of the smem index (keeps quads aligned)
-  const int nz_beg = int(k0 - k0a);
-  const int nz_end = int(k1 - k0a);
+  const int64_t kq0 = k0 & ~int64_t(3); // aligned origin of the shared-memory index
+  const int nslots = int(((k1 - kq0) + 3) & ~int64_t(3));
+  T* s_prod = reinterpret_cast<T*>(dyn_smem);
+  int* s_rowend = reinterpret_cast<int*>(dyn_smem + ((size_t(nslots + 4) * sizeof(T) + 15) & ~size_t(15)));
+  const int nz_beg = int(k0 - kq0);
+  const int nz_end = int(k1 - kq0);
 
   if (tid == 0)
     s_nlong = 0;
 
   // ---- phase 1: row ends ----------------------------------------------------
   for (int q = tid; q < nr; q += THREADS)
-    s_rowend[q] = int(int64_t(ld_stream(rowptr + row0 + 1 + q)) - k0a);
+    s_rowend[q] = int(int64_t(ld_stream(rowptr + row0 + 1 + q)) - kq0);
 
-  // ---- phase 2: products ------------------------------------------------------
-  int64_t ka, kb; // [k0,ka) scalar head, [ka,kb) aligned quads, [kb,k1) scalar tail
-  if (vec_ok) {
-    ka = (k0 + 3) & ~int64_t(3);
-    if (ka > k1)
-      ka = k1;
-    kb = k1 & ~int64_t(3);
-    if (kb < ka)
-      kb = ka;
-  } else {
-    ka = k1;
-    kb = k1;
-  }
+  // ---- phase 2: products, quad by quad over the aligned superset ----------------
+  // A quad that lies inside the arrays is fetched with 128-bit streaming loads even
+  // when it straddles the tile boundary (the neighbours' elements are masked out);
+  // only the arrays' last partial quad, or unaligned arrays, take scalar loads.
   {
-    const int nq = int((kb - ka) >> 2);
-    Quad<I> c[QITER];
-    Quad<T> v[QITER];
-    // issue every streaming load of this thread before the first dependent gather
+    const int nq = nslots >> 2;
+    for (int q0 = 0; q0 < nq; q0 += 2 * THREADS) {
+      Quad<I> c[2];
+      Quad<T> v[2];
 #pragma unroll
-    for (int it = 0; it < QITER; ++it) {
-      const int q = tid + it * THREADS;
-      if (q < nq) {
-        const int64_t k = ka + 4 * int64_t(q);
-        c[it] = ld_stream_quad(colind + k);
-        if (perm == nullptr) {
-          v[it] = ld_stream_quad(values + k);
-        } else {
-          const Quad<O> pi = ld_stream_quad(perm + k);
+      for (int u = 0; u < 2; ++u) {
+        const int q = q0 + tid + u * THREADS;
+        if (q < nq) {
+          const int64_t k = kq0 + 4 * int64_t(q);
+          if (vec_ok && k + 4 <= nnz_end) {
+            c[u] = ld_stream_quad(colind + k);
+            if (perm == nullptr) {
+              v[u] = ld_stream_quad(values + k);
+            } else {
+              const Quad<O> pi = ld_stream_quad(perm + k);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            v[it].v[j] = ld_ro(values + pi.v[j]);
+              for (int j = 0; j < 4; ++j)
+                v[u].v[j] = (k + j >= k0 && k + j < k1) ? ld_ro(values + pi.v[j]) : T(0);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool ok = k + j >= k0 && k + j < k1;
+              c[u].v[j] = ok ? ld_stream(colind + k + j) : I(0);
+              v[u].v[j] = !ok ? T(0)
+                              : (perm == nullptr ? ld_stream(values + k + j)
+                                                 : ld_ro(values + perm[k + j]));
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int q = q0 + tid + u * THREADS;
+        if (q < nq) {
+          const int64_t k = kq0 + 4 * int64_t(q);
+          Vec4<T> p;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool ok = k + j >= k0 && k + j < k1;
+            p.v[j] = ok ? v[u].v[j] * ld_ro(x + c[u].v[j]) : T(0);
+          }
+          *reinterpret_cast<Vec4<T>*>(&s_prod[k - kq0]) = p;
         }
       }
     }
-#pragma unroll
-    for (int it = 0; it < QITER; ++it) {
-      const int q = tid + it * THREADS;
-      if (q < nq) {
-        Vec4<T> p;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          p.v[j] = v[it].v[j] * ld_ro(x + c[it].v[j]);
-        const int64_t k = ka + 4 * int64_t(q);
-        *reinterpret_cast<Vec4<T>*>(&s_prod[k - k0a]) = p;
-      }
-    }
-  }
-  // scalar head and tail (at most 3 elements each when vec_ok)
-  for (int64_t k = k0 + tid; k < ka; k += THREADS) {
-    const T a = perm == nullptr ? ld_stream(values + k) : ld_ro(values + perm[k]);
-    s_prod[k - k0a] = a * ld_ro(x + ld_stream(colind + k));
-  }
-  for (int64_t k = kb + tid; k < k1; k += THREADS) {
-    const T a = perm == nullptr ? ld_stream(values + k) : ld_ro(values + perm[k]);
-    s_prod[k - k0a] = a * ld_ro(x + ld_stream(colind + k));
   }
   __syncthreads();
 
@@ -245,21 +823,77 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
   const auto aligned16 = [](const void* q) {
     return (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
   };
-  const int vec_ok = aligned16(p->csr_colind) && aligned16(values) &&
-                     (p->csr_perm == nullptr || aligned16(p->csr_perm));
+  const bool perm = p->csr_perm != nullptr;
+  const int vec_ok = aligned16(p->csr_colind) && (perm || aligned16(values)) &&
+                     (!perm || aligned16(p->csr_perm));
   if (p->num_tiles > int64_t(0x7fffffff))
     return fail(p, SPBLAS_B200_NOT_SUPPORTED, "too many tiles for one launch");
-  spmv_merge_tile_kernel<T, I, O>
-      <<<unsigned(p->num_tiles), kSpmvThreads, 0, p->stream>>>(
-          static_cast<const O*>(p->csr_rowptr),
-          static_cast<const I*>(p->csr_colind), static_cast<const T*>(values),
-          static_cast<const O*>(p->csr_perm), static_cast<const T*>(x),
-          static_cast<T*>(y), a, static_cast<const int64_t*>(p->tile_starts.p),
-          p->csr_rows, static_cast<int64_t*>(p->carry_row.p),
-          static_cast<T*>(p->carry_val.p), vec_ok);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess)
-    return cuda_fail(p, e, "spmv_merge_tile_kernel");
+  const int64_t nnz_end = p->base + p->nnz;
+
+  int variant = p->forced_variant >= 0 ? p->forced_variant : kVariantPipelined;
+  if (!vec_ok)
+    variant = kVariantMergeTile; // bulk copies need 16-byte aligned arrays
+  p->spmv_variant = variant;
+
+  cudaError_t e;
+  if (variant == kVariantPipelined) {
+    // Pipeline shape: stages x (header + tile data) of shared memory per CTA; shared
+    // memory decides how many CTAs fit per SM.
+    const int data_bytes = pipe_stage_data_bytes(p->tile_items, sizeof(T), sizeof(I),
+                                                 sizeof(O), perm);
+    const size_t per_stage = size_t(kPipeHeaderBytes) + size_t(data_bytes);
+    const size_t budget = 227 * 1024;
+    int ctas_per_sm = p->ctas_per_sm > 0 ? p->ctas_per_sm : (p->consumer_warps == 16 ? 1 : 3);
+    int stages = p->stages > 0 ? p->stages : 3;
+    if (stages > kPipeMaxStages)
+      stages = kPipeMaxStages;
+    if (stages < 2)
+      stages = 2;
+    while (ctas_per_sm > 1 && (128 + 3 * per_stage + 1024) * ctas_per_sm > budget)
+      --ctas_per_sm; // never trade the third stage for occupancy
+    while (stages > 2 && (128 + stages * per_stage + 1024) * ctas_per_sm > budget)
+      --stages;
+    const size_t smem = 128 + size_t(stages) * per_stage;
+    const int cw = p->consumer_warps == 16 ? 16 : 8;
+    int64_t grid = int64_t(p->num_sms) * ctas_per_sm;
+    if (grid > p->num_tiles)
+      grid = p->num_tiles;
+    auto launch = [&](auto kern, int threads) -> cudaError_t {
+      cudaError_t e2 = cudaFuncSetAttribute(
+          kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e2 != cudaSuccess)
+        return e2;
+      kern<<<unsigned(grid), threads, smem, p->stream>>>(
+          static_cast<const O*>(p->csr_rowptr), static_cast<const I*>(p->csr_colind),
+          static_cast<const T*>(values), static_cast<const O*>(p->csr_perm),
+          static_cast<const T*>(x), static_cast<T*>(y), a,
+          static_cast<const int64_t*>(p->tile_starts.p),
+          static_cast<const int*>(p->tile_uniform.p), p->num_tiles, p->csr_rows, nnz_end,
+          static_cast<int64_t*>(p->carry_row.p), static_cast<T*>(p->carry_val.p), stages,
+          data_bytes, p->debug_mode);
+      return cudaGetLastError();
+    };
+    e = cw == 16 ? launch(spmv_pipe_kernel<T, I, O, 16>, 16 * 32 + 32)
+                 : launch(spmv_pipe_kernel<T, I, O, 8>, 8 * 32 + 32);
+    if (e != cudaSuccess)
+      return cuda_fail(p, e, "spmv_pipe_kernel");
+  } else {
+    const size_t cap = size_t(p->tile_items) + kTileSlack;
+    const size_t smem = ((cap * sizeof(T) + 15) & ~size_t(15)) + cap * sizeof(int) + 64;
+    auto kern = spmv_merge_tile_kernel<T, I, O>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess)
+      return cuda_fail(p, e, "cudaFuncSetAttribute(spmv_merge_tile_kernel)");
+    kern<<<unsigned(p->num_tiles), kSpmvThreads, smem, p->stream>>>(
+        static_cast<const O*>(p->csr_rowptr), static_cast<const I*>(p->csr_colind),
+        static_cast<const T*>(values), static_cast<const O*>(p->csr_perm),
+        static_cast<const T*>(x), static_cast<T*>(y), a,
+        static_cast<const int64_t*>(p->tile_starts.p), p->csr_rows, nnz_end,
+        static_cast<int64_t*>(p->carry_row.p), static_cast<T*>(p->carry_val.p), vec_ok);
+    e = cudaGetLastError();
+    if (e != cudaSuccess)
+      return cuda_fail(p, e, "spmv_merge_tile_kernel");
+  }
   const unsigned fgrid = unsigned((p->num_tiles + 255) / 256);
   spmv_carry_fixup_kernel<T><<<fgrid, 256, 0, p->stream>>>(
       static_cast<const int64_t*>(p->carry_row.p),
@@ -291,7 +925,6 @@ int dispatch_index(spblas_b200_plan* p, const void* alpha, const void* values,
 int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
              const void* values, const void* x, void* y) {
   p->last_launches = 0;
-  p->spmv_variant = kVariantMergeTile;
   switch (val_type) {
   case SPBLAS_B200_F32:
     return dispatch_index<float>(p, alpha, values, x, y);
