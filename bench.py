@@ -375,7 +375,7 @@ def main():
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic("c2"),
-                "kernel": "spmv_merge_tile_kernel<double,int,int> (+ carry fix-up, ~1% of the step)",
+                "kernel": "spmv_pipe_kernel<double,int,int,8> (+ carry fix-up kernel, ~2% of the step)",
                 "algorithmic_bytes_per_launch": bytes_launch, "kernel_ms": kern_ms,
                 "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0,

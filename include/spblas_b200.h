@@ -96,7 +96,9 @@ enum {
   SPBLAS_B200_Q_CSR_PERM = 11,      /* offset_t[nnz]:   value gather permutation (CSC only)    */
   SPBLAS_B200_Q_NUM_SEGMENTS = 12,  /* int64[1]: SpMM row segments (0 = rows are not split)    */
   SPBLAS_B200_Q_SEGMENTS = 13,      /* int64[3*num_segments]: (row, nnz_begin, nnz_end)        */
-  SPBLAS_B200_Q_SPMM_VARIANT = 14   /* int64[1]: kernel variant of the last SpMM               */
+  SPBLAS_B200_Q_SPMM_VARIANT = 14,  /* int64[1]: kernel variant of the last SpMM               */
+  SPBLAS_B200_Q_TILE_UNIFORM = 15   /* int32[num_tiles]: common length L (1..8) of a tile's
+                                       complete rows after the first, 0 if they differ          */
 };
 
 /* Row-length histogram: bin 0 = empty rows, bin b >= 1 = rows with
@@ -123,7 +125,8 @@ SPBLAS_B200_API int spblas_b200_plan_set_stream(spblas_b200_plan* plan,
      - validates the offsets array (monotone; ptr[0] may be any base >= 0, as a
        row-block shard of a larger matrix has; ptr[last]-ptr[0] must equal nnz),
      - row-length histogram, max row length, empty-row count,
-     - merge-path partition table over (row ends + nonzeros),
+     - merge-path partition table over (row ends + nonzeros), and per tile whether
+       its complete rows all have one length (stencils: no row-end lookups at execute),
      - CSC: builds the row-major (CSR) image of A by a stable counting sort:
        rowptr/colind of the transpose-of-the-storage plus a value permutation,
      - SpMM (k_hint > 1): row segments for rows longer than the segment limit.

@@ -174,6 +174,17 @@ def merge_partition(rowptr, tile_items):
     return starts.reshape(-1, 2)
 
 
+def tile_uniform(rowptr, starts, max_len=8):
+    rp = _c(rowptr, np.int64)
+    st = _c(np.asarray(starts).reshape(-1), np.int64)
+    nt = len(st) // 2 - 1
+    out = np.zeros(max(nt, 1), dtype=np.int32)
+    fn = lib().oracle_tile_uniform
+    fn.restype = None
+    fn(_p(rp), _p(st), C.c_int64(nt), C.c_int(max_len), _p(out))
+    return out[:nt]
+
+
 def row_segments(rowptr, seg):
     rp = _c(rowptr, np.int64)
     fn = lib().oracle_row_segments

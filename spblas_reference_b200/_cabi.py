@@ -22,7 +22,7 @@ F32, F64, S32 = 0, 1, 2
 INSPECT_DEFAULT, INSPECT_LIGHT = 0, 1
 (Q_NUM_TILES, Q_TILE_ITEMS, Q_TILE_STARTS, Q_ROWLEN_HIST, Q_MAX_ROW_LEN, Q_EMPTY_ROWS,
  Q_SPMV_VARIANT, Q_LAST_LAUNCHES, Q_TOTAL_LAUNCHES, Q_CSR_ROWPTR, Q_CSR_COLIND,
- Q_CSR_PERM, Q_NUM_SEGMENTS, Q_SEGMENTS, Q_SPMM_VARIANT) = range(15)
+ Q_CSR_PERM, Q_NUM_SEGMENTS, Q_SEGMENTS, Q_SPMM_VARIANT, Q_TILE_UNIFORM) = range(16)
 HIST_BINS = 40
 
 # every symbol include/spblas_b200.h declares (tests/test_cabi_symbols.py checks the

@@ -374,6 +374,8 @@ int spblas_b200_plan_query(spblas_b200_plan* p, int what, void* out,
   case SPBLAS_B200_Q_TILE_STARTS:
     return device_array(p->tile_starts.p,
                         size_t(p->num_tiles + 1) * 2 * sizeof(int64_t));
+  case SPBLAS_B200_Q_TILE_UNIFORM:
+    return device_array(p->tile_uniform.p, size_t(p->num_tiles) * sizeof(int));
   case SPBLAS_B200_Q_ROWLEN_HIST: {
     const size_t n = sizeof(int64_t) * SPBLAS_B200_HIST_BINS;
     if (needed)

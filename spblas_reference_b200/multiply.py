@@ -91,6 +91,8 @@ class operation_info_t:
     @property
     def tile_starts(self): return self._query_array(_cabi.Q_TILE_STARTS, np.int64).reshape(-1, 2)
     @property
+    def tile_uniform(self): return self._query_array(_cabi.Q_TILE_UNIFORM, np.int32)
+    @property
     def rowlen_hist(self): return self._query_array(_cabi.Q_ROWLEN_HIST, np.int64)
     @property
     def max_row_len(self): return self._query_scalar(_cabi.Q_MAX_ROW_LEN)

@@ -1,0 +1,337 @@
+// dropin_test.cpp — the B200 backend used through the UNMODIFIED reference API:
+//   #include <spblas/spblas.hpp> compiled with -DSPBLAS_ENABLE_B200 against the reference's
+//   own headers (+ integration/enable_b200.patch) and include/spblas/vendor/b200/.
+// gtest is not available offline, so this is a small self-contained harness.  The cases
+// re-host what the reference's GPU contract test checks
+// (test/gtest/device/spmv_test.cpp:11-146: SpMV, SpMV_Ascaled, SpMV_BScaled on util::dims with
+// generate_csr seed 0, judged by EXPECT_EQ_ of test/gtest/util.hpp:7-23) and add what the
+// reference has no device test for: SpMM (cf. test/gtest/spmm_test.cpp:6-221), CSC,
+// transposed(), matrix_opt, multiply_inspect + multiply(info, ..) / multiply_execute, fp64,
+// 64-bit offsets, and the error behaviour.
+#include <spblas/spblas.hpp>
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <limits>
+#include <span>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+namespace {
+
+int g_checks = 0, g_failures = 0;
+std::string g_case;
+
+void fail(const std::string& what) {
+  ++g_failures;
+  std::printf("  FAIL [%s] %s\n", g_case.c_str(), what.c_str());
+}
+
+#define CUDA_OK(expr)                                                              \
+  do {                                                                             \
+    cudaError_t e__ = (expr);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      std::printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__,  \
+                  __LINE__);                                                       \
+      std::exit(2);                                                                \
+    }                                                                              \
+  } while (0)
+
+// the reference tests' acceptance criterion (test/gtest/util.hpp:7-23)
+template <typename T>
+bool close_enough(T t, T u) {
+  if constexpr (std::is_floating_point_v<T>) {
+    const T eps = 64 * std::numeric_limits<T>::epsilon();
+    const T norm = std::min(std::abs(t) + std::abs(u), std::numeric_limits<T>::max());
+    return std::abs(t - u) <= std::max(std::numeric_limits<T>::min(), eps * norm);
+  } else {
+    return t == u;
+  }
+}
+
+template <typename T>
+void expect_all_close(const std::vector<T>& ref, const std::vector<T>& got) {
+  ++g_checks;
+  if (ref.size() != got.size()) {
+    fail("size mismatch");
+    return;
+  }
+  for (std::size_t i = 0; i < ref.size(); ++i) {
+    if (!close_enough(ref[i], got[i])) {
+      fail("element " + std::to_string(i) + ": expected " + std::to_string(ref[i]) +
+           ", got " + std::to_string(got[i]));
+      return;
+    }
+  }
+}
+
+template <typename T>
+class device_array {
+public:
+  device_array() = default;
+  explicit device_array(const std::vector<T>& h) : n_(h.size()) {
+    CUDA_OK(cudaMalloc(&p_, std::max<std::size_t>(n_, 1) * sizeof(T)));
+    if (n_)
+      CUDA_OK(cudaMemcpy(p_, h.data(), n_ * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  device_array(std::size_t n, T fill) : device_array(std::vector<T>(n, fill)) {}
+  device_array(const device_array&) = delete;
+  device_array& operator=(const device_array&) = delete;
+  ~device_array() {
+    if (p_)
+      cudaFree(p_);
+  }
+  T* get() const { return p_; }
+  std::size_t size() const { return n_; }
+  std::vector<T> to_host() const {
+    std::vector<T> h(n_);
+    if (n_)
+      CUDA_OK(cudaMemcpy(h.data(), p_, n_ * sizeof(T), cudaMemcpyDeviceToHost));
+    return h;
+  }
+
+private:
+  T* p_ = nullptr;
+  std::size_t n_ = 0;
+};
+
+const std::vector<std::tuple<int, int, int>> dims = {
+    {1000, 100, 100}, {100, 1000, 10000}, {40, 40, 1000}}; // util::dims
+
+template <typename T, typename I, typename O>
+std::vector<T> host_spmv(int m, const std::vector<O>& rowptr, const std::vector<I>& colind,
+                         const std::vector<T>& values, const std::vector<T>& x, T alpha) {
+  std::vector<T> y(m, 0);
+  for (int i = 0; i < m; ++i)
+    for (O p = rowptr[i]; p < rowptr[i + 1]; ++p)
+      y[i] += alpha * values[p] * x[colind[p]];
+  return y;
+}
+
+template <typename T, typename I, typename O>
+std::vector<T> host_spmm(int m, int k, const std::vector<O>& rowptr,
+                         const std::vector<I>& colind, const std::vector<T>& values,
+                         const std::vector<T>& B, T alpha) {
+  std::vector<T> C(std::size_t(m) * k, 0);
+  for (int i = 0; i < m; ++i)
+    for (O p = rowptr[i]; p < rowptr[i + 1]; ++p)
+      for (int j = 0; j < k; ++j)
+        C[std::size_t(i) * k + j] += alpha * values[p] * B[std::size_t(colind[p]) * k + j];
+  return C;
+}
+
+// ---- SpMV: the three reference device tests + inspect/execute reuse ------------------
+template <typename T, typename I, typename O>
+void spmv_cases() {
+  for (auto [m, n, nnz] : dims) {
+    auto [values, rowptr, colind, shape, nnz_] = spblas::generate_csr<T, I, O>(m, n, nnz);
+    std::vector<T> x(n, 1);
+    device_array<T> d_values(values);
+    device_array<O> d_rowptr(rowptr);
+    device_array<I> d_colind(colind);
+    device_array<T> d_x(x);
+    device_array<T> d_y(m, std::numeric_limits<T>::quiet_NaN()); // stale y must vanish
+    spblas::csr_view<T, I, O> a(d_values.get(), d_rowptr.get(), d_colind.get(), shape,
+                                O(nnz));
+    std::span<T> x_span(d_x.get(), n);
+    std::span<T> y_span(d_y.get(), m);
+
+    g_case = "SpMV";
+    spblas::multiply(a, x_span, y_span);
+    expect_all_close(host_spmv<T, I, O>(m, rowptr, colind, values, x, T(1)), d_y.to_host());
+
+    for (int alpha : {-10, 1, 5}) {
+      g_case = "SpMV_Ascaled";
+      spblas::multiply(spblas::scaled(alpha, a), x_span, y_span);
+      expect_all_close(host_spmv<T, I, O>(m, rowptr, colind, values, x, T(alpha)),
+                       d_y.to_host());
+      g_case = "SpMV_BScaled";
+      spblas::multiply(a, spblas::scaled(alpha, x_span), y_span);
+      expect_all_close(host_spmv<T, I, O>(m, rowptr, colind, values, x, T(alpha)),
+                       d_y.to_host());
+    }
+
+    g_case = "SpMV inspect/execute";
+    auto info = spblas::multiply_inspect(a, x_span, y_span);
+    for (int rep = 0; rep < 3; ++rep) {
+      spblas::multiply(info, spblas::scaled(2.0f, a), x_span, y_span);
+      expect_all_close(host_spmv<T, I, O>(m, rowptr, colind, values, x, T(2)),
+                       d_y.to_host());
+    }
+    spblas::multiply_execute(info, a, x_span, y_span);
+    expect_all_close(host_spmv<T, I, O>(m, rowptr, colind, values, x, T(1)), d_y.to_host());
+    spblas::operation_info_t moved = std::move(info); // move-only state travels
+    spblas::multiply(moved, a, x_span, y_span);
+    expect_all_close(host_spmv<T, I, O>(m, rowptr, colind, values, x, T(1)), d_y.to_host());
+
+    g_case = "SpMV matrix_opt";
+    spblas::matrix_opt a_opt(a);
+    auto info2 = spblas::multiply_inspect(a_opt, x_span, y_span);
+    spblas::multiply(info2, a_opt, x_span, y_span);
+    expect_all_close(host_spmv<T, I, O>(m, rowptr, colind, values, x, T(1)), d_y.to_host());
+  }
+}
+
+// ---- CSC and transposed() -----------------------------------------------------------------
+void csc_cases() {
+  using T = float;
+  using I = spblas::index_t;
+  using O = spblas::offset_t;
+  for (auto [m, n, nnz] : dims) {
+    auto [values, colptr, rowind, shape, nnz_] = spblas::generate_csc<T, I, O>(m, n, nnz);
+    std::vector<T> x(n);
+    for (int j = 0; j < n; ++j)
+      x[j] = T(1 + j % 3);
+    std::vector<T> ref(m, 0);
+    for (int j = 0; j < n; ++j)
+      for (O p = colptr[j]; p < colptr[j + 1]; ++p)
+        ref[rowind[p]] += values[p] * x[j];
+    device_array<T> d_values(values);
+    device_array<O> d_colptr(colptr);
+    device_array<I> d_rowind(rowind);
+    device_array<T> d_x(x), d_y(m, T(-1));
+    spblas::csc_view<T, I, O> a(d_values.get(), d_colptr.get(), d_rowind.get(), shape, O(nnz));
+    std::span<T> x_span(d_x.get(), n), y_span(d_y.get(), m);
+    g_case = "CscView SpMV";
+    spblas::multiply(a, x_span, y_span);
+    expect_all_close(ref, d_y.to_host());
+    auto info = spblas::multiply_inspect(a, x_span, y_span);
+    spblas::multiply(info, a, x_span, y_span);
+    expect_all_close(ref, d_y.to_host());
+
+    // transposed(csr) is the csc over the same arrays (algorithms/transposed.hpp:7-13):
+    // read the colptr/rowind arrays as the CSR of A^T (n x m) and transpose that view
+    // back, which must give A again
+    g_case = "transposed";
+    spblas::csr_view<T, I, O> at_csr(d_values.get(), d_colptr.get(), d_rowind.get(),
+                                     spblas::index<I>(I(n), I(m)), O(nnz));
+    auto a_again = spblas::transposed(at_csr);
+    device_array<T> d_y2(m, T(0));
+    spblas::multiply(a_again, x_span, std::span<T>(d_y2.get(), m));
+    expect_all_close(ref, d_y2.to_host());
+    // and the CSR view itself computes A^T x2
+    std::vector<T> x2(m, 1), ref2(n, 0);
+    for (int j = 0; j < n; ++j)
+      for (O p = colptr[j]; p < colptr[j + 1]; ++p)
+        ref2[j] += values[p] * x2[rowind[p]];
+    device_array<T> d_x2(x2), d_y3(n, T(0));
+    spblas::multiply(at_csr, std::span<T>(d_x2.get(), m), std::span<T>(d_y3.get(), n));
+    expect_all_close(ref2, d_y3.to_host());
+  }
+}
+
+// ---- SpMM ---------------------------------------------------------------------------------------
+template <typename T>
+void spmm_cases() {
+  using I = spblas::index_t;
+  for (auto [m, k, nnz] : dims) {
+    for (int n : {1, 8, 32, 64, 512}) {
+      auto [values, rowptr, colind, shape, nnz_] = spblas::generate_csr<T, I>(m, k, nnz);
+      auto [b_values, b_shape] = spblas::generate_dense<T>(k, n);
+      device_array<T> d_values(values);
+      device_array<I> d_rowptr(rowptr), d_colind(colind);
+      device_array<T> d_b(b_values), d_c(std::size_t(m) * n, std::numeric_limits<T>::quiet_NaN());
+      spblas::csr_view<T, I> a(d_values.get(), d_rowptr.get(), d_colind.get(), shape, I(nnz));
+      spblas::mdspan_row_major<T, I> b(d_b.get(), k, n);
+      spblas::mdspan_row_major<T, I> c(d_c.get(), m, n);
+
+      g_case = "SpMM n=" + std::to_string(n);
+      spblas::multiply(a, b, c);
+      expect_all_close(host_spmm<T, I, I>(m, n, rowptr, colind, values, b_values, T(1)),
+                       d_c.to_host());
+      g_case = "SpMM_AScaled n=" + std::to_string(n);
+      spblas::multiply(spblas::scaled(2.0f, a), b, c);
+      expect_all_close(host_spmm<T, I, I>(m, n, rowptr, colind, values, b_values, T(2)),
+                       d_c.to_host());
+      g_case = "SpMM_BScaled n=" + std::to_string(n);
+      spblas::multiply(a, spblas::scaled(2.0f, b), c);
+      expect_all_close(host_spmm<T, I, I>(m, n, rowptr, colind, values, b_values, T(2)),
+                       d_c.to_host());
+      g_case = "SpMM_Aopt n=" + std::to_string(n);
+      spblas::matrix_opt a_opt(a);
+      auto info = spblas::multiply_inspect(a_opt, b, c); // examples/spmm_csr.cpp:45-46
+      spblas::multiply(info, a_opt, b, c);
+      expect_all_close(host_spmm<T, I, I>(m, n, rowptr, colind, values, b_values, T(1)),
+                       d_c.to_host());
+      spblas::multiply_execute(info, a_opt, b, c);
+      expect_all_close(host_spmm<T, I, I>(m, n, rowptr, colind, values, b_values, T(1)),
+                       d_c.to_host());
+    }
+  }
+}
+
+void csc_spmm_case() {
+  using T = float;
+  using I = spblas::index_t;
+  auto [m, k, nnz] = dims[1];
+  const int n = 32;
+  auto [values, colptr, rowind, shape, nnz_] = spblas::generate_csc<T, I>(m, k, nnz);
+  auto [b_values, b_shape] = spblas::generate_dense<T>(k, n);
+  std::vector<T> ref(std::size_t(m) * n, 0);
+  for (int j = 0; j < k; ++j)
+    for (I p = colptr[j]; p < colptr[j + 1]; ++p)
+      for (int c = 0; c < n; ++c)
+        ref[std::size_t(rowind[p]) * n + c] += values[p] * b_values[std::size_t(j) * n + c];
+  device_array<T> d_values(values), d_b(b_values), d_c(std::size_t(m) * n, T(0));
+  device_array<I> d_colptr(colptr), d_rowind(rowind);
+  spblas::csc_view<T, I> a(d_values.get(), d_colptr.get(), d_rowind.get(), shape, I(nnz));
+  g_case = "CscView SpMM";
+  spblas::multiply(a, spblas::mdspan_row_major<T, I>(d_b.get(), k, n),
+                   spblas::mdspan_row_major<T, I>(d_c.get(), m, n));
+  expect_all_close(ref, d_c.to_host());
+}
+
+// ---- error behaviour --------------------------------------------------------------------------
+void error_cases() {
+  using T = float;
+  using I = spblas::index_t;
+  auto [values, rowptr, colind, shape, nnz] = spblas::generate_csr<T, I>(40, 40, 100);
+  device_array<T> d_values(values), d_x(41, T(1)), d_y(40, T(0));
+  device_array<I> d_rowptr(rowptr), d_colind(colind);
+  spblas::csr_view<T, I> a(d_values.get(), d_rowptr.get(), d_colind.get(), shape, nnz);
+  g_case = "shape mismatch";
+  ++g_checks;
+  try {
+    spblas::multiply(a, std::span<T>(d_x.get(), 41), std::span<T>(d_y.get(), 40));
+    fail("no exception for a vector of the wrong length");
+  } catch (const std::invalid_argument& e) {
+    if (std::string(e.what()) != "multiply: matrix and vector dimensions are incompatible.")
+      fail(std::string("unexpected message: ") + e.what());
+  }
+  g_case = "conjugated view";
+  ++g_checks;
+  try {
+    spblas::multiply(spblas::conjugated(a), std::span<T>(d_x.get(), 40),
+                     std::span<T>(d_y.get(), 40));
+    fail("no exception for a conjugated view");
+  } catch (const std::runtime_error&) {
+  }
+}
+
+} // namespace
+
+int main() {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    std::printf("dropin_test: no CUDA device\n");
+    return 77;
+  }
+  static_assert(std::is_same_v<spblas::index_t, std::int32_t>,
+                "the B200 backend sets 32-bit default indices like the other GPU backends");
+  spmv_cases<float, spblas::index_t, spblas::offset_t>(); // the reference's device test types
+  spmv_cases<double, std::int32_t, std::int64_t>();
+  spmv_cases<float, std::int64_t, std::int64_t>();
+  csc_cases();
+  spmm_cases<float>();
+  spmm_cases<double>();
+  csc_spmm_case();
+  error_cases();
+  std::printf("dropin_test: %d checks, %d failures\n", g_checks, g_failures);
+  return g_failures == 0 ? 0 : 1;
+}

@@ -126,6 +126,7 @@ def test_inspect_structures_bit_exact(cuda, oracle, kind):
     want = oracle.merge_partition(rp, tile)
     assert info.num_tiles == len(want) - 1
     assert np.array_equal(info.tile_starts, want)
+    assert np.array_equal(info.tile_uniform, oracle.tile_uniform(rp, want))
     segs = oracle.row_segments(rp, 4096)
     assert info.num_segments == len(segs)
     if len(segs):
@@ -225,6 +226,9 @@ def test_c2_poisson_known_answer_and_iteration(cuda, oracle):
     x = torch.ones(n, dtype=torch.float64, device=cuda)
     y = torch.empty(n, dtype=torch.float64, device=cuda)
     info = sb.multiply_inspect(a, x, y)
+    tu = info.tile_uniform
+    assert np.array_equal(tu, oracle.tile_uniform(rp.cpu().numpy(), info.tile_starts))
+    assert (tu == 5).mean() > 0.6                          # interior tiles take the stencil path
     sb.multiply(info, a, x, y)
     # A * 1 = 4 - (number of neighbours): exact small integers
     i, j = torch.arange(n, device=cuda) // g, torch.arange(n, device=cuda) % g

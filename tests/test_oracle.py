@@ -173,6 +173,21 @@ def test_merge_partition_properties(oracle, kind, tile):
             assert k <= rp[r + 1]
 
 
+def test_tile_uniform(oracle):
+    rp = np.arange(0, 5 * 1001, 5, dtype=np.int64)           # 1000 rows of 5
+    st = oracle.merge_partition(rp, 64)
+    tu = oracle.tile_uniform(rp, st)
+    assert (tu == 5).all()
+    rp2 = rp.copy()
+    rp2[500:] += 1                                            # row 499 has 6 entries
+    st2 = oracle.merge_partition(rp2, 64)
+    tu2 = oracle.tile_uniform(rp2, st2)
+    bad = [t for t in range(len(tu2)) if st2[t, 0] + 1 <= 499 < st2[t + 1, 0]]
+    assert len(bad) == 1 and tu2[bad[0]] == 0 and (np.delete(tu2, bad) == 5).all()
+    rp3 = np.arange(0, 9 * 200, 9, dtype=np.int64)            # rows of 9: longer than the cap
+    assert (oracle.tile_uniform(rp3, oracle.merge_partition(rp3, 64)) == 0).all()
+
+
 def test_rowlen_hist_and_segments(oracle):
     rng = np.random.default_rng(5)
     rp = _random_rowptr(rng, 4000, "hub")
