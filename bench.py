@@ -43,7 +43,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2",
-                    choices=["c1", "c2", "c3k32", "c3k128", "c4"])
+                    choices=["c1", "c2", "c3k32", "c3k128", "c4", "c5"])
+    ap.add_argument("--scale", type=int, default=0,
+                    help="C5 R-MAT scale (default 24 + log2(N): 16.7M rows per GPU)")
     ap.add_argument("--grid", type=int, default=4096, help="C2 grid edge (per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -249,6 +251,13 @@ def main():
     K, W = max(1, args.steps), max(3, args.warmup)
     peak, peak_src = measured_peak()
 
+    if args.workload == "c5":
+        from bench_extra import run_c5   # R-MAT fp64 / int64 offsets, nnz-balanced row blocks
+        run_c5(args, sb, G, dev, peak, peak_src, ClockSampler(local_rank), world, rank,
+               barrier, max_over_ranks, sum_over_ranks)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload != "c2":
         from bench_extra import run_extra   # single-GPU side workloads (C1, C3, C4)
         run_extra(args, sb, G, dev, peak, peak_src, ClockSampler(local_rank))

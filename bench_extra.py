@@ -111,3 +111,89 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         "clocks": clocks, "gpu_launches": int(launches - W * (launches // (K + W)) if False else launches),
     }
     print(json.dumps(line), flush=True)
+
+
+def run_c5(args, sb, G, dev, peak, peak_src, sampler, world, rank, barrier, max_over_ranks,
+           sum_over_ranks):
+    """C5: R-MAT (edge factor 16) CSR SpMV fp64 with int32 indices and int64 offsets,
+    nnz-balanced row blocks over the ranks, x replicated, iterated y -> x with an allgather
+    of the blocks (sharded.py picks it: an R-MAT block references almost every column).
+    Weak-scaled by default: scale = 24 + log2(N) (scale 27 at N = 8, as BASELINE.json)."""
+    import math
+    from spblas_reference_b200.sharded import ShardedSpMV, balanced_nnz_blocks
+    K, W = max(1, args.steps), max(3, args.warmup)
+    scale = args.scale if args.scale > 0 else 24 + int(round(math.log2(world)))
+    n = 1 << scale
+    deg = G.rmat_degrees(scale, 16, seed=27, device=dev)
+    rowptr_all = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(deg, 0, out=rowptr_all[1:])
+    blocks = balanced_nnz_blocks(rowptr_all, world)
+    max_deg = int(deg.max())
+    del deg, rowptr_all
+    r0, r1 = blocks[rank]
+    v, rp, ci, shape = G.rmat_csr(scale, 16, seed=27, dtype=torch.float64, device=dev,
+                                  off_dtype=torch.int64, row_begin=r0, row_end=r1)
+    m_loc, nnz_loc = shape[0], int(ci.numel())
+    a = sb.csr_view(v, rp, ci, shape, nnz_loc)
+    alpha = 1.0 / max_deg                          # keeps the iterates in [0, 1]
+    a_scaled = sb.scaled(alpha, a)
+    x0 = G.dense_uniform((n,), 5, torch.float64, dev)
+    y0 = torch.empty(m_loc, dtype=torch.float64, device=dev)
+    t0 = time.perf_counter()
+    info = sb.multiply_inspect(a, x0, y0)
+    torch.cuda.synchronize()
+    inspect_ms = (time.perf_counter() - t0) * 1e3
+    op = ShardedSpMV(n, blocks, (0, n), lambda x, y: sb.multiply_execute(info, a_scaled, x, y),
+                     torch.float64, dev)
+    op.set_x(x0)
+    del x0, y0
+    for _ in range(W):
+        op.step()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = info.total_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        op.step()
+    e1.record()
+    barrier()
+    step_ms = max_over_ranks(e0.elapsed_time(e1) / K)
+    launches = int(sum_over_ranks(info.total_launches - l0))
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    k0.record()
+    for _ in range(K):
+        op.multiply()
+    k1.record()
+    barrier()
+    kern_ms = max_over_ranks(k0.elapsed_time(k1) / K)
+    clocks = sampler.stop() if rank == 0 else None
+    total_nnz = int(sum_over_ranks(nnz_loc))
+    nbytes = nnz_loc * 12 + (m_loc + 1) * 8 + n * 8 + m_loc * 8   # full replicated x (SURVEY 8d)
+    achieved = nbytes / (kern_ms * 1e-3) / 1e9
+    if rank == 0:
+        line = {
+            "metric": "CSR SpMV GFLOP/s", "value": 2.0 * total_nnz / (step_ms * 1e-3) / 1e9,
+            "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"C5 R-MAT scale {scale} (edge factor 16) CSR SpMV fp64, int32 "
+                                   "indices, int64 offsets, nnz-balanced row blocks, iterated "
+                                   "y->x with allgather", "nnz": total_nnz,
+                       "rows_rank0": m_loc, "nnz_rank0": nnz_loc, "exchange": op.plan.mode,
+                       "kernel_only_ms": kern_ms, "inspect_ms": inspect_ms,
+                       "max_row_len": info.max_row_len, "spmv_variant": info.spmv_variant,
+                       "l2_policy": "inputs larger than L2"},
+            "gbs": achieved,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
+                         "note": "random 8-byte gathers of x (1 GB at scale 27) cost a 32-byte "
+                                 "sector each: the compulsory-bytes roofline is not reachable "
+                                 "(SURVEY 8d caveat)"},
+            "clocks": clocks, "gpu_launches": launches,
+        }
+        print(json.dumps(line), flush=True)

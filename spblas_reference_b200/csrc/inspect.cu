@@ -25,7 +25,7 @@ namespace b200 {
 
 namespace {
 
-constexpr int kStatsWords = SPBLAS_B200_HIST_BINS + 4; // hist, max, flags, nseg, nsplit
+constexpr int kStatsWords = SPBLAS_B200_HIST_BINS + 5; // hist, max, flags, nseg, nsplit, uniform tiles
 
 // ---------------------------------------------------------------------------
 // 1. row-length histogram
@@ -128,7 +128,8 @@ template <typename O>
 __global__ void __launch_bounds__(256)
 tile_uniform_kernel(const O* __restrict__ rowptr,
                     const int64_t* __restrict__ tile_starts, int64_t num_tiles,
-                    int max_len, int* __restrict__ out) {
+                    int max_len, int* __restrict__ out,
+                    unsigned long long* __restrict__ uniform_count) {
   const int64_t t = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (t >= num_tiles)
@@ -143,8 +144,11 @@ tile_uniform_kernel(const O* __restrict__ rowptr,
       ok = ok && (int64_t(rowptr[r + 1]) - int64_t(rowptr[r]) == L);
   }
   ok = __all_sync(0xffffffffu, ok);
-  if (lane == 0)
+  if (lane == 0) {
     out[t] = ok ? int(L) : 0;
+    if (ok)
+      atomicAdd(uniform_count, 1ull);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -306,9 +310,17 @@ int inspect_rows(spblas_b200_plan* p, const O* rowptr, int64_t rows, int flags) 
     const int grid = int((nthreads + 255) / 256);
     tile_uniform_kernel<O><<<grid, 256, 0, s>>>(
         rowptr, static_cast<const int64_t*>(p->tile_starts.p), p->num_tiles, 8,
-        static_cast<int*>(p->tile_uniform.p));
+        static_cast<int*>(p->tile_uniform.p), d_stats + SPBLAS_B200_HIST_BINS + 4);
     if (int e = launch_ok(p, "tile_uniform_kernel"))
       return e;
+    // how many tiles take the stencil path decides which SpMV kernel runs
+    unsigned long long nuni = 0;
+    B200_CUDA_TRY(p, cudaMemcpyAsync(&nuni, d_stats + SPBLAS_B200_HIST_BINS + 4,
+                                     sizeof(nuni), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+    p->uniform_tiles = int64_t(nuni);
+  } else {
+    p->uniform_tiles = 0;
   }
 
   if (!light && rows > 0) {

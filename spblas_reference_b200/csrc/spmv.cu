@@ -830,7 +830,14 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
     return fail(p, SPBLAS_B200_NOT_SUPPORTED, "too many tiles for one launch");
   const int64_t nnz_end = p->base + p->nnz;
 
-  int variant = p->forced_variant >= 0 ? p->forced_variant : kVariantPipelined;
+  // Kernel choice.  The pipelined kernel wins when most tiles are uniform (stencils,
+  // fixed-degree graphs: coalesced row-ordered gathers, no row-end lookups); matrices
+  // with mixed row lengths are bound by random gathers of x, where the one-tile-per-CTA
+  // kernel's higher occupancy (64 warps/SM of gathers in flight) is worth more.
+  int variant = p->forced_variant >= 0
+                    ? p->forced_variant
+                    : (2 * p->uniform_tiles >= p->num_tiles ? kVariantPipelined
+                                                            : kVariantMergeTile);
   if (!vec_ok)
     variant = kVariantMergeTile; // bulk copies need 16-byte aligned arrays
   p->spmv_variant = variant;

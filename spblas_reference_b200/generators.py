@@ -115,6 +115,19 @@ def rmat_edges(scale: int, edge_begin: int, edge_end: int, seed: int, device,
     return row, col
 
 
+def rmat_degrees(scale: int, edge_factor: int, seed: int, device, chunk_edges: int = 1 << 26):
+    """Row degrees of the R-MAT graph (one pass over the edges, no storage): what a rank
+    needs to cut nnz-balanced row blocks before it generates its own block."""
+    n = 1 << scale
+    total = edge_factor * n
+    deg = torch.zeros(n, dtype=torch.int64, device=device)
+    for b in range(0, total, chunk_edges):
+        r, _ = rmat_edges(scale, b, min(total, b + chunk_edges), seed, device)
+        deg += torch.bincount(r, minlength=n)
+        del r
+    return deg
+
+
 def rmat_csr(scale: int, edge_factor: int, seed: int, dtype=torch.float32, device="cpu",
              off_dtype=torch.int32, chunk_edges: int = 1 << 26, row_begin: int = 0,
              row_end: Optional[int] = None):
