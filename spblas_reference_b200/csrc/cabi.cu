@@ -149,8 +149,6 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->ctas_per_sm = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_CONSUMER_WARPS"))
     p->consumer_warps = std::atoi(v);
-  if (const char* v = std::getenv("SPBLAS_B200_DEBUG_MODE"))
-    p->debug_mode = std::atoi(v);
   *out = p;
   return SPBLAS_B200_SUCCESS;
 }

@@ -79,7 +79,6 @@ struct spblas_b200_plan {
   int stages = 0;              // env SPBLAS_B200_STAGES (0 = default)
   int ctas_per_sm = 0;         // env SPBLAS_B200_CTAS_PER_SM (0 = default)
   int consumer_warps = 0;      // env SPBLAS_B200_CONSUMER_WARPS (8 or 16; 0 = default)
-  int debug_mode = 0;          // env SPBLAS_B200_DEBUG_MODE (1: stream only, 2: no copies) — wrong results
   int64_t num_tiles = 0;
   int64_t uniform_tiles = 0;      // tiles whose complete rows share one length <= 8
   b200::DeviceBuffer tile_starts; // int64 (row, nnz) pairs, num_tiles + 1 entries

@@ -56,67 +56,92 @@ __device__ __forceinline__ void store_c(T* p, const BVec<T, VEC>& r) {
   }
 }
 
-// Accumulate alpha-less products of the nonzeros [kb, ke) of one row into acc.
-template <typename T, typename I, typename O, int VEC, int LANES>
+// Entries of A held per lane for one chunk of a row: a group of LANES lanes keeps
+// LANES * kEntries(LANES) (colind, value) pairs in registers.
+template <int LANES>
+struct ChunkShape {
+  static constexpr int E = LANES >= 16 ? 1 : (LANES == 8 ? 2 : 4);
+  static constexpr int CHUNK = LANES * E;
+};
+
+// coalesced load of the chunk [kk, min(kk + CHUNK, ke)) of a row: entry e of the chunk
+// lives in slot e / LANES of lane e % LANES
+template <typename T, typename I, typename O, int LANES>
 __device__ __forceinline__ void
-accumulate_row(const I* __restrict__ colind, const T* __restrict__ values,
-               const O* __restrict__ perm, const T* __restrict__ B,
-               const int64_t ldb, const int64_t kb, const int64_t ke,
-               const int64_t c0, const bool active, const int lane,
-               const unsigned gmask, T (&acc)[VEC]) {
-  constexpr int BATCH = LANES < 8 ? LANES : 8;
-  for (int64_t kk = kb; kk < ke; kk += LANES) {
-    I myc = I(0);
-    T myv = T(0);
-    if (kk + lane < ke) {
-      myc = ld_stream(colind + kk + lane);
-      myv = perm == nullptr ? ld_stream(values + kk + lane)
-                            : ld_ro(values + perm[kk + lane]);
+load_chunk(const I* __restrict__ colind, const T* __restrict__ values,
+           const O* __restrict__ perm, int64_t kk, int64_t ke, int lane,
+           I (&c)[ChunkShape<LANES>::E], T (&v)[ChunkShape<LANES>::E]) {
+#pragma unroll
+  for (int sl = 0; sl < ChunkShape<LANES>::E; ++sl) {
+    const int64_t idx = kk + sl * LANES + lane;
+    c[sl] = I(0);
+    v[sl] = T(0);
+    if (idx < ke) {
+      c[sl] = ld_stream(colind + idx);
+      v[sl] = perm == nullptr ? ld_stream(values + idx) : ld_ro(values + perm[idx]);
     }
-    const int cnt = ke - kk < LANES ? int(ke - kk) : LANES;
+  }
+}
+
+// acc += sum over the first `cnt` entries of the chunk of value * B[col, c0 : c0+VEC]
+template <typename T, typename I, int VEC, int LANES>
+__device__ __forceinline__ void
+process_chunk(const I (&c)[ChunkShape<LANES>::E], const T (&v)[ChunkShape<LANES>::E],
+              int cnt, const T* __restrict__ B, int64_t ldb, int64_t c0, bool active,
+              unsigned gmask, T (&acc)[VEC]) {
+  constexpr int CHUNK = ChunkShape<LANES>::CHUNK;
+  constexpr int BATCH = CHUNK < 8 ? CHUNK : 8;
 #pragma unroll
-    for (int j0 = 0; j0 < LANES; j0 += BATCH) {
-      if (j0 < cnt) {
-        BVec<T, VEC> b[BATCH];
-        T v[BATCH];
+  for (int j0 = 0; j0 < CHUNK; j0 += BATCH) {
+    if (j0 < cnt) { // group-uniform
+      BVec<T, VEC> b[BATCH];
+      T a[BATCH];
 #pragma unroll
-        for (int j = 0; j < BATCH; ++j) {
-          const I c = __shfl_sync(gmask, myc, j0 + j, LANES);
-          v[j] = __shfl_sync(gmask, myv, j0 + j, LANES);
-          // Slots past the end of the row must not touch B at all: a NaN/Inf in
-          // an unreferenced B row may not leak into C (0 * NaN), exactly as the
-          // reference never reads it.  They contribute 0 * 0.
-          if (active && j0 + j < cnt) {
-            b[j] = load_b<T, VEC>(B + int64_t(c) * ldb + c0);
-          } else {
+      for (int j = 0; j < BATCH; ++j) {
+        const int e = j0 + j;
+        const I col = __shfl_sync(gmask, c[e / LANES], e % LANES, LANES);
+        a[j] = __shfl_sync(gmask, v[e / LANES], e % LANES, LANES);
+        // Slots past the end of the row must not touch B at all: a NaN/Inf in an
+        // unreferenced B row may not leak into C (0 * NaN), exactly as the reference
+        // never reads it.  They contribute 0 * 0.
+        if (active && e < cnt) {
+          b[j] = load_b<T, VEC>(B + int64_t(col) * ldb + c0);
+        } else {
 #pragma unroll
-            for (int u = 0; u < VEC; ++u)
-              b[j].v[u] = T(0);
-          }
+          for (int u = 0; u < VEC; ++u)
+            b[j].v[u] = T(0);
         }
-        if (active) {
+      }
+      if (active) {
 #pragma unroll
-          for (int j = 0; j < BATCH; ++j)
+        for (int j = 0; j < BATCH; ++j)
 #pragma unroll
-            for (int u = 0; u < VEC; ++u)
-              acc[u] += v[j] * b[j].v[u];
-        }
+          for (int u = 0; u < VEC; ++u)
+            acc[u] += a[j] * b[j].v[u];
       }
     }
   }
 }
 
-template <typename T, typename I, typename O, int VEC, int LANES>
-__global__ void __launch_bounds__(kSpmmThreads)
+// Persistent, software-pipelined: every group walks rows row0, row0 + stride, ...  While
+// the B rows of the current A row are being gathered, the loads for the FUTURE are
+// already in flight — the row offsets of the row two steps ahead and the first chunk of
+// (colind, value) pairs of the next row — so that a row costs one round of memory
+// latency (the B gather) instead of three (offsets -> pairs -> B).
+template <typename T, typename I, typename O, int VEC, int LANES, int MINB>
+__global__ void __launch_bounds__(kSpmmThreads, MINB)
 spmm_row_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
                 const T* __restrict__ values, const O* __restrict__ perm,
                 const T* __restrict__ B, const int64_t ldb, T* __restrict__ C,
                 const int64_t ldc, const T alpha, const int64_t rows,
                 const int64_t k, const int64_t seg_limit) {
   constexpr int GROUPS = kSpmmThreads / LANES;
+  constexpr int E = ChunkShape<LANES>::E;
+  constexpr int CHUNK = ChunkShape<LANES>::CHUNK;
   const int lane = threadIdx.x % LANES;
   const int grp = threadIdx.x / LANES;
-  const int64_t row = int64_t(blockIdx.x) * GROUPS + grp;
+  const int64_t stride = int64_t(gridDim.x) * GROUPS;
+  int64_t row = int64_t(blockIdx.x) * GROUPS + grp;
   if (row >= rows)
     return; // the whole group leaves together
   const int64_t c0 = (int64_t(blockIdx.y) * LANES + lane) * VEC;
@@ -125,23 +150,63 @@ spmm_row_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
       LANES == 32 ? 0xffffffffu
                   : (((1u << LANES) - 1u) << (((threadIdx.x & 31) / LANES) * LANES));
 
-  const int64_t kb = int64_t(rowptr[row]), ke = int64_t(rowptr[row + 1]);
-  T acc[VEC];
+  int64_t kb = int64_t(rowptr[row]), ke = int64_t(rowptr[row + 1]);
+  int64_t kb1 = 0, ke1 = 0;
+  if (row + stride < rows) {
+    kb1 = int64_t(rowptr[row + stride]);
+    ke1 = int64_t(rowptr[row + stride + 1]);
+  }
+  I pc[E];
+  T pv[E];
+  load_chunk<T, I, O, LANES>(colind, values, perm, kb, ke, lane, pc, pv);
+
+  for (; row < rows; row += stride) {
+    // ---- loads for the future ----------------------------------------------------------
+    int64_t kb2 = 0, ke2 = 0;
+    if (row + 2 * stride < rows) {
+      kb2 = int64_t(rowptr[row + 2 * stride]);
+      ke2 = int64_t(rowptr[row + 2 * stride + 1]);
+    }
+    I nc[E];
+    T nv[E];
+    load_chunk<T, I, O, LANES>(colind, values, perm, kb1, ke1, lane, nc, nv);
+
+    // ---- the current row ---------------------------------------------------------------
+    // rows cut into segments are produced by spmm_segment_kernel + combine
+    if (ke - kb <= seg_limit) {
+      T acc[VEC];
 #pragma unroll
-  for (int u = 0; u < VEC; ++u)
-    acc[u] = T(0);
-  // rows cut into segments are produced by spmm_segment_kernel + combine
-  if (ke - kb <= seg_limit)
-    accumulate_row<T, I, O, VEC, LANES>(colind, values, perm, B, ldb, kb, ke, c0,
-                                        active, lane, gmask, acc);
-  else
-    return;
-  if (active) {
-    BVec<T, VEC> out;
+      for (int u = 0; u < VEC; ++u)
+        acc[u] = T(0);
+      int64_t rem = ke - kb;
+      process_chunk<T, I, VEC, LANES>(pc, pv, rem < CHUNK ? int(rem) : CHUNK, B, ldb, c0,
+                                      active, gmask, acc);
+      for (int64_t kk = kb + CHUNK; kk < ke; kk += CHUNK) {
+        I tc[E];
+        T tv[E];
+        load_chunk<T, I, O, LANES>(colind, values, perm, kk, ke, lane, tc, tv);
+        rem = ke - kk;
+        process_chunk<T, I, VEC, LANES>(tc, tv, rem < CHUNK ? int(rem) : CHUNK, B, ldb, c0,
+                                        active, gmask, acc);
+      }
+      if (active) {
+        BVec<T, VEC> out;
 #pragma unroll
-    for (int u = 0; u < VEC; ++u)
-      out.v[u] = alpha * acc[u];
-    store_c<T, VEC>(C + row * ldc + c0, out);
+        for (int u = 0; u < VEC; ++u)
+          out.v[u] = alpha * acc[u];
+        store_c<T, VEC>(C + row * ldc + c0, out);
+      }
+    }
+    // ---- rotate the pipeline -------------------------------------------------------------
+    kb = kb1;
+    ke = ke1;
+    kb1 = kb2;
+    ke1 = ke2;
+#pragma unroll
+    for (int sl = 0; sl < E; ++sl) {
+      pc[sl] = nc[sl];
+      pv[sl] = nv[sl];
+    }
   }
 }
 
@@ -168,8 +233,15 @@ spmm_segment_kernel(const int64_t* __restrict__ segments,
 #pragma unroll
   for (int u = 0; u < VEC; ++u)
     acc[u] = T(0);
-  accumulate_row<T, I, O, VEC, LANES>(colind, values, perm, B, ldb, kb, ke, c0,
-                                      active, lane, gmask, acc);
+  for (int64_t kk = kb; kk < ke; kk += ChunkShape<LANES>::CHUNK) {
+    I tc[ChunkShape<LANES>::E];
+    T tv[ChunkShape<LANES>::E];
+    load_chunk<T, I, O, LANES>(colind, values, perm, kk, ke, lane, tc, tv);
+    const int64_t rem = ke - kk;
+    process_chunk<T, I, VEC, LANES>(
+        tc, tv, rem < ChunkShape<LANES>::CHUNK ? int(rem) : ChunkShape<LANES>::CHUNK, B, ldb,
+        c0, active, gmask, acc);
+  }
   if (active) {
     // the partial workspace is dense: row s, leading dimension k
 #pragma unroll
@@ -211,13 +283,25 @@ int launch_spmm(spblas_b200_plan* p, const T alpha, const void* values,
       p->num_segments > 0 ? kSpmmSegment : int64_t(0x7fffffffffffffff);
   int launches = 0;
   if (row_blocks > 0) {
-    const dim3 grid{unsigned(row_blocks), unsigned(col_tiles), 1u};
-    spmm_row_kernel<T, I, O, VEC, LANES><<<grid, kSpmmThreads, 0, p->stream>>>(
-        static_cast<const O*>(p->csr_rowptr), static_cast<const I*>(p->csr_colind),
-        static_cast<const T*>(values), static_cast<const O*>(p->csr_perm),
-        static_cast<const T*>(B), ldb, static_cast<T*>(C), ldc, alpha, rows, k,
-        seg_limit);
-    cudaError_t e = cudaGetLastError();
+    // persistent: as many CTAs as are resident at once, each group walking rows
+    auto go = [&](auto kern) -> cudaError_t {
+      int per_sm = 0;
+      cudaError_t eo =
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSpmmThreads, 0);
+      if (eo != cudaSuccess || per_sm < 1)
+        per_sm = 2;
+      const int64_t resident = int64_t(p->num_sms) * per_sm;
+      const int64_t gx = row_blocks < resident ? row_blocks : resident;
+      const dim3 grid{unsigned(gx), unsigned(col_tiles), 1u};
+      kern<<<grid, kSpmmThreads, 0, p->stream>>>(
+          static_cast<const O*>(p->csr_rowptr), static_cast<const I*>(p->csr_colind),
+          static_cast<const T*>(values), static_cast<const O*>(p->csr_perm),
+          static_cast<const T*>(B), ldb, static_cast<T*>(C), ldc, alpha, rows, k, seg_limit);
+      return cudaGetLastError();
+    };
+    // three resident CTAs per SM (<= 80 registers) measured best on C3: two lose
+    // gathers in flight, four spill
+    cudaError_t e = go(spmm_row_kernel<T, I, O, VEC, LANES, 3>);
     if (e != cudaSuccess)
       return cuda_fail(p, e, "spmm_row_kernel");
     ++launches;

@@ -300,7 +300,7 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
                  const int* __restrict__ tile_uniform, const int64_t num_tiles,
                  const int64_t rows, const int64_t nnz_end,
                  int64_t* __restrict__ carry_row, T* __restrict__ carry_val,
-                 const int stages, const int stage_data_bytes, const int debug_mode) {
+                 const int stages, const int stage_data_bytes) {
   constexpr int kPipeConsumerWarps = CW;        // consumer warps; warp CW is the producer
   constexpr int kPipeConsumers = CW * 32;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -473,10 +473,7 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
 
     int tb; // local index where the trailing partial row starts
     bool tail_from_prod;
-    if (debug_mode == 1) {
-      tb = hi; // tuning aid: stream only
-      tail_from_prod = true;
-    } else if (uni > 0 && nr > 0) {
+    if (uni > 0 && nr > 0) {
       // ---- path 1: uniform tile ----------------------------------------------------
       const T* val = prod; // !has_perm: values are staged at off_prod == off_b
       const int e0 = int(rowend[0] - kq0);
@@ -877,7 +874,7 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
           static_cast<const int64_t*>(p->tile_starts.p),
           static_cast<const int*>(p->tile_uniform.p), p->num_tiles, p->csr_rows, nnz_end,
           static_cast<int64_t*>(p->carry_row.p), static_cast<T*>(p->carry_val.p), stages,
-          data_bytes, p->debug_mode);
+          data_bytes);
       return cudaGetLastError();
     };
     e = cw == 16 ? launch(spmv_pipe_kernel<T, I, O, 16>, 16 * 32 + 32)
