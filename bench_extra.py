@@ -98,6 +98,10 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
     launches = launches_of() - l0
     clocks = sampler.stop()
     achieved = nbytes / (ms * 1e-3) / 1e9
+    from bench import ncu_traffic
+    traffic = ncu_traffic(wl)
+    if wl.startswith("c3"):
+        extra["spmm_variant"] = info.spmm_variant
     line = {
         "metric": "CSR SpMM GFLOP/s" if wl.startswith("c3") else "CSR SpMV GFLOP/s",
         "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": 1, "steps": K,
@@ -106,8 +110,11 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         "config": dict(workload=name, nnz=nnz, **extra),
         "gbs": achieved,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
-                     "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src},
+                     "frac": achieved / peak, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
+                     # what the launch really moved through DRAM (ncu), per second: for the
+                     # gather-bound configs THIS is what sits against the HBM peak
+                     "dram_gbs_at_ncu_traffic": (traffic / (ms * 1e-3) / 1e9) if traffic else None},
         "clocks": clocks, "gpu_launches": int(launches - W * (launches // (K + W)) if False else launches),
     }
     print(json.dumps(line), flush=True)

@@ -63,7 +63,8 @@ void release_all(spblas_b200_plan* p) {
                           &p->sort_tmp0,   &p->sort_tmp1,  &p->sort_tmp2,
                           &p->sort_ws,     &p->tile_starts, &p->tile_uniform, &p->carry_row,
                           &p->carry_val,   &p->segments,   &p->seg_partial,
-                          &p->seg_counter, &p->stats};
+                          &p->seg_counter, &p->stats,      &p->spmm_starts,
+                          &p->spmm_carry_row, &p->spmm_carry_val};
   for (DeviceBuffer* b : bufs)
     release(*b);
 }
@@ -136,6 +137,9 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     return SPBLAS_B200_CUDA_ERROR;
   }
   p->num_sms = sms > 0 ? sms : 148;
+  int l2 = 0;
+  if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, p->device) == cudaSuccess && l2 > 0)
+    p->l2_bytes = l2;
   if (const char* v = std::getenv("SPBLAS_B200_SPMV_VARIANT"))
     p->forced_variant = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_TILE_ITEMS")) {
@@ -149,6 +153,12 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->ctas_per_sm = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_CONSUMER_WARPS"))
     p->consumer_warps = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_SPMM_VARIANT"))
+    p->spmm_forced = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_SPMM_CTAS_PER_SM"))
+    p->spmm_ctas_per_sm = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_SPMM_L2FRAC"))
+    p->spmm_l2_fraction = float(std::atof(v));
   *out = p;
   return SPBLAS_B200_SUCCESS;
 }

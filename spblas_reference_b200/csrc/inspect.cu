@@ -523,12 +523,42 @@ int inspect_typed(spblas_b200_plan* p, int flags) {
   return SPBLAS_B200_SUCCESS;
 }
 
+template <typename O>
+int stream_partition_typed(spblas_b200_plan* p, int64_t streams) {
+  const int64_t total = p->csr_rows + p->nnz;
+  int64_t items = (total + streams - 1) / streams;
+  if (items < 1)
+    items = 1;
+  if (items > int64_t(0x7fffffff))
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "SpMM stream too long");
+  if (int rc = reserve(p, p->spmm_starts, size_t(streams + 1) * 2 * sizeof(int64_t)))
+    return rc;
+  if (int rc = reserve(p, p->spmm_carry_row, size_t(streams) * sizeof(int64_t)))
+    return rc;
+  const int grid = int((streams + 1 + 255) / 256);
+  merge_partition_kernel<O><<<grid, 256, 0, p->stream>>>(
+      static_cast<const O*>(p->csr_rowptr), p->csr_rows, p->nnz, p->base, int(items), streams,
+      static_cast<int64_t*>(p->spmm_starts.p));
+  if (int e = launch_ok(p, "merge_partition_kernel (SpMM streams)"))
+    return e;
+  p->spmm_streams = streams;
+  return SPBLAS_B200_SUCCESS;
+}
+
 } // namespace
+
+// The SpMM stream table: the same merge-path cut as the SpMV tiles, but into exactly
+// `streams` runs (one per resident warp of spmm_ring_kernel).
+int build_stream_partition(spblas_b200_plan* p, int64_t streams) {
+  return p->off_type == SPBLAS_B200_I64 ? stream_partition_typed<int64_t>(p, streams)
+                                        : stream_partition_typed<int32_t>(p, streams);
+}
 
 int inspect_structure(spblas_b200_plan* p, int flags) {
   const bool i64 = p->idx_type == SPBLAS_B200_I64;
   const bool o64 = p->off_type == SPBLAS_B200_I64;
   int rc;
+  p->spmm_streams = 0; // the stream table belongs to the previous structure
   if (!i64 && !o64)
     rc = inspect_typed<int32_t, int32_t>(p, flags);
   else if (!i64 && o64)

@@ -51,6 +51,7 @@ struct spblas_b200_plan {
   cudaStream_t stream = nullptr;
   int device = 0;
   int num_sms = 148;
+  int64_t l2_bytes = 126ll << 20;
 
   // ---- structure as given by the caller (not owned) -------------------------
   bool inspected = false;
@@ -93,6 +94,17 @@ struct spblas_b200_plan {
   b200::DeviceBuffer seg_partial;  // partial C rows of split rows (num_segments x k)
   b200::DeviceBuffer seg_counter;  // int64 scratch
 
+  // ---- SpMM streams (spmm_ring_kernel) ------------------------------------------
+  // The merged sequence (row ends ++ nonzeros) cut into `spmm_streams` equal runs,
+  // one per resident warp; stream w covers [spmm_starts[w], spmm_starts[w+1]).
+  int64_t spmm_streams = 0;          // 0: table not built
+  b200::DeviceBuffer spmm_starts;    // int64 (row, nnz) pairs, spmm_streams + 1 entries
+  b200::DeviceBuffer spmm_carry_row; // int64 per stream: row the stream's tail belongs to, or -1
+  b200::DeviceBuffer spmm_carry_val; // spmm_streams x k partial C rows
+  int spmm_forced = -1;              // env SPBLAS_B200_SPMM_VARIANT: 0 group kernel, 1 stream kernel
+  int spmm_ctas_per_sm = 0;          // env SPBLAS_B200_SPMM_CTAS_PER_SM (0 = what fits)
+  float spmm_l2_fraction = -1.f;     // env SPBLAS_B200_SPMM_L2FRAC: share of B kept evict_last (<0: auto)
+
   // ---- statistics -------------------------------------------------------------
   bool have_hist = false;
   int64_t hist[SPBLAS_B200_HIST_BINS] = {0};
@@ -126,6 +138,7 @@ void release(DeviceBuffer& b);
 
 // inspect.cu
 int inspect_structure(spblas_b200_plan* p, int flags);
+int build_stream_partition(spblas_b200_plan* p, int64_t streams);
 // spmv.cu
 int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
              const void* values, const void* x, void* y);

@@ -134,3 +134,45 @@ def test_c3_shape_reduced(cuda, oracle, k):
     C_ref = oracle.spmm("csr", shape, rph, cih, vh, Bh)
     # all operands are non-negative here, so sum |a b| is the reference result itself
     assert_rows_within_bound(C.cpu().numpy(), C_ref, rph, C_ref.astype(np.float64), f"C3 k={k}")
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("k", [1, 5, 16, 32, 48, 64, 100, 128, 256])
+@pytest.mark.parametrize("vt", [np.float32, np.float64])
+def test_spmm_both_kernels_every_width(cuda, oracle, monkeypatch, variant, k, vt):
+    """The group kernel (0) and the stream kernel (1) forced at every width: skewed row
+    lengths (empty runs, a hub row spanning many streams), offsets with a non-zero base."""
+    monkeypatch.setenv("SPBLAS_B200_SPMM_VARIANT", str(variant))
+    rng = np.random.default_rng(1000 + k)
+    m, n = 2311, 1777
+    lens = rng.integers(0, 30, size=m)
+    lens[rng.integers(0, m, size=m // 3)] = 0
+    lens[100:400] = 0                                            # a long run of empty rows
+    lens[1500] = 9000                                            # hub: shared by many streams
+    lens[m - 1] = 77
+    base = 123
+    rp = (np.concatenate([[0], np.cumsum(lens)]) + base).astype(np.int32)
+    nnz = int(rp[-1]) - base
+    ci_full = rng.integers(0, n, size=nnz + base).astype(np.int32)
+    v_full = rng.standard_normal(nnz + base).astype(vt)
+    B = rng.standard_normal((n, k)).astype(vt)
+    a = sb.csr_view(dev(v_full), dev(rp), dev(ci_full), (m, n), nnz)
+    Bd = dev(B)
+    Cd = torch.full((m, k), float("nan"), dtype=Bd.dtype, device="cuda")
+    info = sb.multiply_inspect(a, Bd, Cd)
+    sb.multiply_execute(info, sb.scaled(0.5, a), Bd, Cd)
+    vec = 16 // np.dtype(vt).itemsize
+    if variant == 1:                 # 16 bytes per lane once C is wider than 256 bytes
+        assert info.spmm_variant == 1000 + (1 if (k * np.dtype(vt).itemsize <= 256 or k % vec) else vec)
+    else:
+        assert info.spmm_variant < 1000
+    rp0 = (rp - base).astype(np.int32)
+    ci, v = ci_full[base:], v_full[base:]
+    C_ref = oracle.spmm("csr", (m, n), rp0, ci, v, B, alpha_a=0.5)
+    assert_rows_within_bound(Cd.cpu().numpy(), C_ref, rp0, spmm_bound(rp0, ci, v, B, 0.5),
+                             f"variant {variant} k={k}")
+    # run to run: bit-identical (no atomics anywhere)
+    C2 = torch.full_like(Cd, float("nan"))
+    sb.multiply_execute(info, sb.scaled(0.5, a), Bd, C2)
+    assert torch.equal(C2, Cd)
+    info.close()
