@@ -284,7 +284,8 @@ def main():
 
     op = ShardedSpMV(n, blocks, (cmin, cmax + 1),
                      lambda x, y: sb.multiply_execute(info, a_scaled, x, y),
-                     torch.float64, dev)
+                     torch.float64, dev, info=info,
+                     fused=None if os.environ.get("SPBLAS_B200_FUSED", "1") != "0" else False)
     op.set_x(x0)
     del x0
 
@@ -324,6 +325,9 @@ def main():
     bytes_launch = spmv_bytes(nnz_loc, m_loc, x_touched, 8, 4, 4)
     achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
 
+    if op.fused:                        # the plan goes back to plain products
+        info.set_scatter(())
+        info.set_barrier((), ())
     # ---- end to end through the public API with HOST buffers --------------------------------
     e2e = None
     if not args.no_e2e:
@@ -377,6 +381,9 @@ def main():
                             "iterated y->x, alpha=1/8 via scaled(); one full product per step",
                 "rows_per_gpu": m_loc, "nnz_per_gpu": nnz_loc, "parallelism": f"rowblock{world}",
                 "exchange": op.plan.mode, "halo_elems_per_step": op.plan.recv_elems,
+                "exchange_impl": ("fused: peer stores from the SpMV kernels + flag barrier in the "
+                                  "fix-up kernel (no collective call)") if op.fused else
+                                 ("nccl" if world > 1 else "none"),
                 "l2_policy": "inputs larger than L2 (1.34 GB per product), no flush",
                 "inspect_ms": inspect_ms,
             },

@@ -150,8 +150,11 @@ def run_c5(args, sb, G, dev, peak, peak_src, sampler, world, rank, barrier, max_
     info = sb.multiply_inspect(a, x0, y0)
     torch.cuda.synchronize()
     inspect_ms = (time.perf_counter() - t0) * 1e3
+    import os
     op = ShardedSpMV(n, blocks, (0, n), lambda x, y: sb.multiply_execute(info, a_scaled, x, y),
-                     torch.float64, dev)
+                     torch.float64, dev, info=info,
+                     fused=None if os.environ.get("SPBLAS_B200_FUSED", "1") != "0" else False,
+                     multicast=os.environ.get("SPBLAS_B200_MULTICAST", "0") == "1")
     op.set_x(x0)
     del x0, y0
     for _ in range(W):
@@ -191,6 +194,9 @@ def run_c5(args, sb, G, dev, peak, peak_src, sampler, world, rank, barrier, max_
                                    "indices, int64 offsets, nnz-balanced row blocks, iterated "
                                    "y->x with allgather", "nnz": total_nnz,
                        "rows_rank0": m_loc, "nnz_rank0": nnz_loc, "exchange": op.plan.mode,
+                       "exchange_impl": ("fused peer stores" + (" (NVLS multicast)" if getattr(op, "multicast", False) else "")
+                                         if op.fused else ("nccl" if world > 1 else "none")),
+                       "fused_error": op.fused_error,
                        "kernel_only_ms": kern_ms, "inspect_ms": inspect_ms,
                        "max_row_len": info.max_row_len, "spmv_variant": info.spmv_variant,
                        "l2_policy": "inputs larger than L2"},

@@ -97,9 +97,14 @@ enum {
   SPBLAS_B200_Q_NUM_SEGMENTS = 12,  /* int64[1]: SpMM row segments (0 = rows are not split)    */
   SPBLAS_B200_Q_SEGMENTS = 13,      /* int64[3*num_segments]: (row, nnz_begin, nnz_end)        */
   SPBLAS_B200_Q_SPMM_VARIANT = 14,  /* int64[1]: kernel variant of the last SpMM               */
-  SPBLAS_B200_Q_TILE_UNIFORM = 15   /* int32[num_tiles]: common length L (1..8) of a tile's
+  SPBLAS_B200_Q_TILE_UNIFORM = 15,  /* int32[num_tiles]: common length L (1..8) of a tile's
                                        complete rows after the first, 0 if they differ          */
+  SPBLAS_B200_Q_BARRIER_EPOCH = 16, /* int64[1]: fused-exchange steps signalled so far         */
+  SPBLAS_B200_Q_BARRIER_TIMEOUT = 17 /* int64[1]: 1 if a fused barrier gave up waiting for a peer */
 };
+
+/* most destinations / peers of a fused exchange (one NVSwitch domain: 8 GPUs) */
+#define SPBLAS_B200_MAX_PEERS 8
 
 /* Row-length histogram: bin 0 = empty rows, bin b >= 1 = rows with
    2^(b-1) <= len < 2^b.  (Row length = rowptr[i+1]-rowptr[i], the definition the
@@ -172,6 +177,36 @@ SPBLAS_B200_API int spblas_b200_spmm_once(
     const void* d_ptr, const void* d_ind, int off_type, int idx_type,
     int val_type, const void* alpha, const void* d_values, const void* d_B,
     int64_t ldb, void* d_C, int64_t ldc, int64_t k);
+
+/* ---- fused exchange for row-block sharded iterations (y -> x) ----------------
+
+   The reference has no multi-GPU path; this is the B200 side of SURVEY.md 8(e).
+   A rank multiplies its row block A[r0:r1, :] against its replica of x; in the
+   iterated use x <- alpha A x every rank then needs (parts of) the other ranks'
+   rows.  Instead of a collective call after the product, the SpMV kernels store
+   the rows a peer needs straight into that peer's buffer over NVLink:
+
+   set_scatter: from now on every spblas_b200_spmv on this plan ALSO stores
+     y[i], for row_begin[d] <= i < row_end[d] (rows of THIS plan's block), to
+     d_dst[d][i] — d_dst[d] is the peer-mapped address at which this block's
+     row 0 lives in destination d's next x (peer's base + r0).  With
+     multicast != 0 the addresses are NVLS multicast addresses and the stores
+     are multimem.st (one store reaches every GPU).  n_dst = 0 switches it off.
+   set_barrier: every spblas_b200_spmv on this plan ends with a flag barrier
+     among the ranks: d_remote_slots[q] is this rank's slot in peer q's flag
+     array (peer-mapped), d_local_slots[q] the slot peer q writes here; flags
+     are uint64 step numbers, zero-initialised by the caller.  Every rank must
+     issue the same sequence of executes.  n_peers = 0 switches it off.
+   Both are properties of the plan (operation_info_t state): multiply /
+   multiply_execute keep the reference's signature. */
+SPBLAS_B200_API int spblas_b200_plan_set_scatter(spblas_b200_plan* plan, int n_dst,
+                                                 void* const* d_dst,
+                                                 const int64_t* row_begin,
+                                                 const int64_t* row_end,
+                                                 int multicast);
+SPBLAS_B200_API int spblas_b200_plan_set_barrier(spblas_b200_plan* plan, int n_peers,
+                                                 void* const* d_remote_slots,
+                                                 const void* const* d_local_slots);
 
 /* ---- introspection / errors ---------------------------------------------- */
 

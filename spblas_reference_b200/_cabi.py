@@ -22,7 +22,9 @@ F32, F64, S32 = 0, 1, 2
 INSPECT_DEFAULT, INSPECT_LIGHT = 0, 1
 (Q_NUM_TILES, Q_TILE_ITEMS, Q_TILE_STARTS, Q_ROWLEN_HIST, Q_MAX_ROW_LEN, Q_EMPTY_ROWS,
  Q_SPMV_VARIANT, Q_LAST_LAUNCHES, Q_TOTAL_LAUNCHES, Q_CSR_ROWPTR, Q_CSR_COLIND,
- Q_CSR_PERM, Q_NUM_SEGMENTS, Q_SEGMENTS, Q_SPMM_VARIANT, Q_TILE_UNIFORM) = range(16)
+ Q_CSR_PERM, Q_NUM_SEGMENTS, Q_SEGMENTS, Q_SPMM_VARIANT, Q_TILE_UNIFORM,
+ Q_BARRIER_EPOCH, Q_BARRIER_TIMEOUT) = range(18)
+MAX_PEERS = 8
 HIST_BINS = 40
 
 # every symbol include/spblas_b200.h declares (tests/test_cabi_symbols.py checks the
@@ -33,6 +35,7 @@ SYMBOLS = (
     "spblas_b200_spmv_once", "spblas_b200_spmm_once", "spblas_b200_plan_query",
     "spblas_b200_last_error", "spblas_b200_last_error_once", "spblas_b200_status_string",
     "spblas_b200_version", "spblas_b200_plan_force_variant",
+    "spblas_b200_plan_set_scatter", "spblas_b200_plan_set_barrier",
 )
 
 
@@ -69,6 +72,11 @@ def lib() -> C.CDLL:
     L.spblas_b200_plan_set_stream.restype = i32
     L.spblas_b200_plan_force_variant.argtypes = [vp, i32]
     L.spblas_b200_plan_force_variant.restype = i32
+    L.spblas_b200_plan_set_scatter.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64),
+                                               C.POINTER(i64), i32]
+    L.spblas_b200_plan_set_scatter.restype = i32
+    L.spblas_b200_plan_set_barrier.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
+    L.spblas_b200_plan_set_barrier.restype = i32
     L.spblas_b200_inspect.argtypes = [vp, i32, i64, i64, i64, vp, vp, i32, i32, i64, i32]
     L.spblas_b200_inspect.restype = i32
     L.spblas_b200_spmv.argtypes = [vp, i32, vp, vp, vp, vp]

@@ -64,7 +64,7 @@ void release_all(spblas_b200_plan* p) {
                           &p->sort_ws,     &p->tile_starts, &p->tile_uniform, &p->carry_row,
                           &p->carry_val,   &p->segments,   &p->seg_partial,
                           &p->seg_counter, &p->stats,      &p->spmm_starts,
-                          &p->spmm_carry_row, &p->spmm_carry_val};
+                          &p->spmm_carry_row, &p->spmm_carry_val, &p->barrier_state};
   for (DeviceBuffer* b : bufs)
     release(*b);
 }
@@ -174,6 +174,58 @@ int spblas_b200_plan_set_stream(spblas_b200_plan* p, void* cuda_stream) {
   if (!p)
     return SPBLAS_B200_INVALID_ARGUMENT;
   p->stream = static_cast<cudaStream_t>(cuda_stream);
+  return SPBLAS_B200_SUCCESS;
+}
+
+int spblas_b200_plan_set_scatter(spblas_b200_plan* p, int n_dst, void* const* d_dst,
+                                 const int64_t* row_begin, const int64_t* row_end,
+                                 int multicast) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  if (n_dst < 0 || n_dst > kMaxPeers)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "at most SPBLAS_B200_MAX_PEERS destinations");
+  if (n_dst > 0 && (!d_dst || !row_begin || !row_end))
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null destination arrays");
+  for (int d = 0; d < n_dst; ++d)
+    if (!d_dst[d] || row_begin[d] < 0 || row_end[d] < row_begin[d])
+      return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "bad scatter destination");
+  p->scatter = ScatterSpec();
+  p->scatter.n = n_dst;
+  p->scatter.multicast = multicast ? 1 : 0;
+  for (int d = 0; d < n_dst; ++d) {
+    p->scatter.dst[d] = d_dst[d];
+    p->scatter.lo[d] = row_begin[d];
+    p->scatter.hi[d] = row_end[d];
+  }
+  return SPBLAS_B200_SUCCESS;
+}
+
+int spblas_b200_plan_set_barrier(spblas_b200_plan* p, int n_peers,
+                                 void* const* d_remote_slots,
+                                 const void* const* d_local_slots) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  if (n_peers < 0 || n_peers > kMaxPeers)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "at most SPBLAS_B200_MAX_PEERS peers");
+  if (n_peers > 0 && (!d_remote_slots || !d_local_slots))
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null flag arrays");
+  p->barrier = BarrierSpec();
+  if (n_peers == 0)
+    return SPBLAS_B200_SUCCESS;
+  for (int d = 0; d < n_peers; ++d) {
+    if (!d_remote_slots[d] || !d_local_slots[d])
+      return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null flag slot");
+    p->barrier.remote[d] = static_cast<unsigned long long*>(d_remote_slots[d]);
+    p->barrier.local[d] = static_cast<const unsigned long long*>(d_local_slots[d]);
+  }
+  if (!p->barrier_state.p) {
+    if (int rc = reserve(p, p->barrier_state, 2 * sizeof(unsigned int)))
+      return rc;
+    B200_CUDA_TRY(p, cudaMemsetAsync(p->barrier_state.p, 0, 2 * sizeof(unsigned int), p->stream));
+  }
+  p->barrier.n = n_peers;
   return SPBLAS_B200_SUCCESS;
 }
 
@@ -364,6 +416,17 @@ int spblas_b200_plan_query(spblas_b200_plan* p, int what, void* out,
     return SPBLAS_B200_SUCCESS;
   };
   switch (what) {
+  case SPBLAS_B200_Q_BARRIER_EPOCH:
+    return scalar(int64_t(p->barrier_epoch));
+  case SPBLAS_B200_Q_BARRIER_TIMEOUT: {
+    unsigned int st[2] = {0, 0};
+    if (p->barrier_state.p) {
+      B200_CUDA_TRY(p, cudaMemcpyAsync(st, p->barrier_state.p, sizeof(st),
+                                       cudaMemcpyDeviceToHost, p->stream));
+      B200_CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    }
+    return scalar(int64_t(st[1]));
+  }
   case SPBLAS_B200_Q_LAST_LAUNCHES:
     return scalar(p->last_launches);
   case SPBLAS_B200_Q_TOTAL_LAUNCHES:

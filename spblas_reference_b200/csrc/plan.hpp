@@ -45,6 +45,25 @@ struct DeviceBuffer {
   size_t cap = 0;
 };
 
+// ---- fused exchange of a row-block sharded iteration (y -> x) ---------------------
+// Rows [lo, hi) of the block this plan multiplies are ALSO stored, by the SpMV kernels
+// themselves, to dst[row]: peer GPUs' replicas of the next x, mapped into this
+// process (NVLink peer memory), or one multicast address (NVLS) that reaches them all.
+constexpr int kMaxPeers = 8;
+struct ScatterSpec {
+  int n = 0;
+  int multicast = 0;
+  void* dst[kMaxPeers] = {};
+  int64_t lo[kMaxPeers] = {}, hi[kMaxPeers] = {};
+};
+// One flag word per peer in every rank's flag array: after its stores a rank writes the
+// step number into its slot on every peer and waits for every peer's number in its own.
+struct BarrierSpec {
+  int n = 0;
+  unsigned long long* remote[kMaxPeers] = {};
+  const unsigned long long* local[kMaxPeers] = {};
+};
+
 } // namespace b200
 
 struct spblas_b200_plan {
@@ -111,6 +130,12 @@ struct spblas_b200_plan {
   int64_t max_row_len = 0;
   int64_t empty_rows = 0;
   b200::DeviceBuffer stats; // device scratch for hist/max/flags
+
+  // ---- fused exchange (set by spblas_b200_plan_set_scatter / _set_barrier) ---------
+  b200::ScatterSpec scatter;
+  b200::BarrierSpec barrier;
+  unsigned long long barrier_epoch = 0; // steps signalled so far
+  b200::DeviceBuffer barrier_state;     // uint32 block counter, uint32 timeout flag
 
   int forced_variant = -1;
   int spmv_variant = b200::kVariantMergeTile;

@@ -123,6 +123,56 @@ __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
 }
 
 // ============================================================================
+// Fused exchange: the kernels that write y also write the rows a peer GPU needs
+// straight into that peer's replica of the next x (NVLink peer stores, or one
+// multimem store that the switch delivers to every GPU), and the carry fix-up
+// kernel ends with the cross-GPU flag barrier — an iteration y -> x is the same two
+// launches as on one GPU, with no collective call.
+// ============================================================================
+template <typename T>
+struct ScatterArgs {
+  int n;
+  int multicast;
+  int64_t lo_min, hi_max; // union of the ranges: tiles outside skip all checks
+  T* dst[kMaxPeers];
+  int64_t lo[kMaxPeers], hi[kMaxPeers];
+};
+
+struct BarrierArgs {
+  int n;
+  unsigned long long epoch;
+  unsigned long long* remote[kMaxPeers];
+  const unsigned long long* local[kMaxPeers];
+  unsigned int* state; // [0] blocks done, [1] timeout flag
+};
+
+template <typename T>
+__device__ __forceinline__ void multimem_store(T* p, T v) {
+  if constexpr (sizeof(T) == 8) {
+    asm volatile("multimem.st.global.f64 [%0], %1;" ::"l"(p),
+                 "d"(*reinterpret_cast<const double*>(&v))
+                 : "memory");
+  } else {
+    asm volatile("multimem.st.global.f32 [%0], %1;" ::"l"(p),
+                 "f"(*reinterpret_cast<const float*>(&v))
+                 : "memory");
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void scatter_store(const ScatterArgs<T>& sc, int64_t row, T v) {
+#pragma unroll 1
+  for (int d = 0; d < sc.n; ++d) {
+    if (row >= sc.lo[d] && row < sc.hi[d]) {
+      if (sc.multicast)
+        multimem_store(sc.dst[d] + row, v);
+      else
+        sc.dst[d][row] = v;
+    }
+  }
+}
+
+// ============================================================================
 // Pipelined kernel
 // ============================================================================
 constexpr int kPipeHeaderBytes = 64;
@@ -184,13 +234,34 @@ __device__ __forceinline__ T dot_exact(const I* __restrict__ col,
   return sum;
 }
 
-template <int L, int CONS, typename T, typename I>
+template <int L, int CONS, bool SCAT, typename T, typename I>
 __device__ __forceinline__ void
 uniform_rows(const I* __restrict__ col, const T* __restrict__ val,
              const T* __restrict__ x, T* __restrict__ yrow, const T alpha, int e0,
-             int nrows, int tid) {
-  for (int r = tid; r < nrows; r += CONS)
-    yrow[r] = alpha * dot_exact<L, T, I>(col, val, x, e0 + L * r);
+             int nrows, int tid, const ScatterArgs<T>& sc, int64_t rowbase) {
+  for (int r = tid; r < nrows; r += CONS) {
+    const T v = alpha * dot_exact<L, T, I>(col, val, x, e0 + L * r);
+    yrow[r] = v;
+    if constexpr (SCAT) // a tile a peer needs rows of (rare: the loop above stays lean)
+      scatter_store(sc, rowbase + r, v);
+  }
+}
+
+template <int CONS, bool SCAT, typename T, typename I>
+__device__ __forceinline__ void
+uniform_tile(int uni, const I* __restrict__ col, const T* __restrict__ val,
+             const T* __restrict__ x, T* __restrict__ yrow, const T alpha, int e0,
+             int nrows, int tid, const ScatterArgs<T>& sc, int64_t rowbase) {
+  switch (uni) {
+  case 1: uniform_rows<1, CONS, SCAT, T, I>(col, val, x, yrow, alpha, e0, nrows, tid, sc, rowbase); break;
+  case 2: uniform_rows<2, CONS, SCAT, T, I>(col, val, x, yrow, alpha, e0, nrows, tid, sc, rowbase); break;
+  case 3: uniform_rows<3, CONS, SCAT, T, I>(col, val, x, yrow, alpha, e0, nrows, tid, sc, rowbase); break;
+  case 4: uniform_rows<4, CONS, SCAT, T, I>(col, val, x, yrow, alpha, e0, nrows, tid, sc, rowbase); break;
+  case 5: uniform_rows<5, CONS, SCAT, T, I>(col, val, x, yrow, alpha, e0, nrows, tid, sc, rowbase); break;
+  case 6: uniform_rows<6, CONS, SCAT, T, I>(col, val, x, yrow, alpha, e0, nrows, tid, sc, rowbase); break;
+  case 7: uniform_rows<7, CONS, SCAT, T, I>(col, val, x, yrow, alpha, e0, nrows, tid, sc, rowbase); break;
+  default: uniform_rows<8, CONS, SCAT, T, I>(col, val, x, yrow, alpha, e0, nrows, tid, sc, rowbase); break;
+  }
 }
 
 // a row (or row fragment) [b, e) by one warp, straight from the staged operands
@@ -300,7 +371,8 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
                  const int* __restrict__ tile_uniform, const int64_t num_tiles,
                  const int64_t rows, const int64_t nnz_end,
                  int64_t* __restrict__ carry_row, T* __restrict__ carry_val,
-                 const int stages, const int stage_data_bytes) {
+                 const int stages, const int stage_data_bytes,
+                 const __grid_constant__ ScatterArgs<T> sc) {
   constexpr int kPipeConsumerWarps = CW;        // consumer warps; warp CW is the producer
   constexpr int kPipeConsumers = CW * 32;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -471,6 +543,14 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
     T* prod = reinterpret_cast<T*>(data + hp->off_prod);
     const O* rowend = reinterpret_cast<const O*>(data + hp->off_rowend);
 
+    // does a peer need rows of this tile?
+    const bool scat = sc.n > 0 && row0 < sc.hi_max && row0 + nr > sc.lo_min;
+    auto put = [&](int64_t row, T v) {
+      y[row] = v;
+      if (scat)
+        scatter_store(sc, row, v);
+    };
+
     int tb; // local index where the trailing partial row starts
     bool tail_from_prod;
     if (uni > 0 && nr > 0) {
@@ -481,20 +561,14 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
       if (warp == 0) {
         const T sum = dot_warp<T, I>(col, val, x, lo, e0, lane);
         if (lane == 0)
-          y[row0] = alpha * sum;
+          put(row0, alpha * sum);
       }
       T* yrow = y + row0 + 1;
       const int nrows = nr - 1;
-      switch (uni) {
-      case 1: uniform_rows<1, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
-      case 2: uniform_rows<2, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
-      case 3: uniform_rows<3, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
-      case 4: uniform_rows<4, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
-      case 5: uniform_rows<5, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
-      case 6: uniform_rows<6, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
-      case 7: uniform_rows<7, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
-      default: uniform_rows<8, kPipeConsumers, T, I>(col, val, x, yrow, alpha, e0, nrows, tid); break;
-      }
+      if (!scat)
+        uniform_tile<kPipeConsumers, false, T, I>(uni, col, val, x, yrow, alpha, e0, nrows, tid, sc, row0 + 1);
+      else
+        uniform_tile<kPipeConsumers, true, T, I>(uni, col, val, x, yrow, alpha, e0, nrows, tid, sc, row0 + 1);
       tb = e0 + uni * nrows;
       tail_from_prod = false;
     } else {
@@ -527,7 +601,7 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
             }
             const bool is_long = e - b > kLongRow;
             if (q < nr && !is_long)
-              y[row0 + q] = alpha * prod_sum_thread(prod, b, e);
+              put(row0 + q, alpha * prod_sum_thread(prod, b, e));
             unsigned todo = __ballot_sync(0xffffffffu, is_long);
             while (todo) {
               const int src = __ffs(todo) - 1;
@@ -536,7 +610,7 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
               const int ee = __shfl_sync(0xffffffffu, e, src);
               const T sum = prod_sum_warp(prod, bb, ee, lane);
               if (lane == 0)
-                y[row0 + q0 + src] = alpha * sum;
+                put(row0 + q0 + src, alpha * sum);
             }
           }
         } else {
@@ -546,7 +620,7 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
             const int e = int(rowend[q] - kq0);
             const T sum = prod_sum_warp(prod, b, e, lane);
             if (lane == 0)
-              y[row0 + q] = alpha * sum;
+              put(row0 + q, alpha * sum);
           }
         }
       }
@@ -620,7 +694,8 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
                        const int64_t* __restrict__ tile_starts,
                        const int64_t rows, const int64_t nnz_end,
                        int64_t* __restrict__ carry_row,
-                       T* __restrict__ carry_val, const int vec_ok) {
+                       T* __restrict__ carry_val, const int vec_ok,
+                       const __grid_constant__ ScatterArgs<T> sc) {
   constexpr int THREADS = kSpmvThreads;
   constexpr int TILE = kSpmvMaxTileItems;
   constexpr int WARPS = THREADS / 32;
@@ -648,6 +723,12 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
 
   if (tid == 0)
     s_nlong = 0;
+  const bool scat = sc.n > 0 && row0 < sc.hi_max && row1 > sc.lo_min;
+  auto put = [&](int64_t row, T v) {
+    y[row] = v;
+    if (scat)
+      scatter_store(sc, row, v);
+  };
 
   // ---- phase 1: row ends ----------------------------------------------------
   for (int q = tid; q < nr; q += THREADS)
@@ -721,7 +802,7 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
           T sum = T(0);
           for (int i = b; i < e; ++i)
             sum += s_prod[i];
-          y[row0 + q] = alpha * sum;
+          put(row0 + q, alpha * sum);
         }
       }
       __syncthreads();
@@ -735,7 +816,7 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
           sum += s_prod[i];
         sum = warp_reduce_sum(sum);
         if (lane == 0)
-          y[row0 + q] = alpha * sum;
+          put(row0 + q, alpha * sum);
       }
     } else {
       // long rows: one warp per row, lanes stride over the row
@@ -747,7 +828,7 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
           sum += s_prod[i];
         sum = warp_reduce_sum(sum);
         if (lane == 0)
-          y[row0 + q] = alpha * sum;
+          put(row0 + q, alpha * sum);
       }
     }
   }
@@ -792,30 +873,71 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
 // Adds the carries of tiles that ended inside a row to that row's y.  A run of
 // consecutive tiles carrying into the same row (a row spanning several tiles) is
 // summed in tile order by the thread of the run's first tile.
+//
+// With a fused exchange this kernel is also where the iteration's cross-GPU barrier
+// lives: the last CTA to finish tells every peer "my rows of step `epoch` are in your
+// x" (a release store at system scope into its slot of the peer's flag array) and
+// waits for the same word from every peer, so that when the stream moves on, the next
+// x is complete here and this rank's old x is no longer being read anywhere.
 template <typename T>
 __global__ void __launch_bounds__(256)
 spmv_carry_fixup_kernel(const int64_t* __restrict__ carry_row,
                         const T* __restrict__ carry_val, int64_t num_tiles,
-                        T* __restrict__ y, const T alpha) {
+                        T* __restrict__ y, const T alpha,
+                        const __grid_constant__ ScatterArgs<T> sc,
+                        const __grid_constant__ BarrierArgs bar) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= num_tiles)
+  if (t < num_tiles) {
+    const int64_t r = carry_row[t];
+    if (r >= 0 && !(t > 0 && carry_row[t - 1] == r)) {
+      T sum = carry_val[t];
+      for (int64_t j = t + 1; j < num_tiles && carry_row[j] == r; ++j)
+        sum += carry_val[j];
+      const T v = y[r] + alpha * sum;
+      y[r] = v;
+      if (sc.n > 0)
+        scatter_store(sc, r, v);
+    }
+  }
+  if (bar.n == 0)
     return;
-  const int64_t r = carry_row[t];
-  if (r < 0)
+  __shared__ bool s_last;
+  __threadfence_system(); // this thread's peer stores, before the count below
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&bar.state[0], 1u);
+    s_last = done == gridDim.x - 1;
+    if (s_last)
+      bar.state[0] = 0; // ready for the next step (stream order protects it)
+  }
+  __syncthreads();
+  if (!s_last || int(threadIdx.x) >= bar.n)
     return;
-  if (t > 0 && carry_row[t - 1] == r)
-    return;
-  T sum = carry_val[t];
-  for (int64_t j = t + 1; j < num_tiles && carry_row[j] == r; ++j)
-    sum += carry_val[j];
-  y[r] += alpha * sum;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(bar.remote[threadIdx.x]),
+               "l"(bar.epoch)
+               : "memory");
+  const long long t0 = clock64();
+  unsigned long long seen = 0;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];"
+                 : "=l"(seen)
+                 : "l"(bar.local[threadIdx.x])
+                 : "memory");
+    if (seen >= bar.epoch)
+      break;
+    if (clock64() - t0 > (1ll << 33)) { // a peer is gone (~4 s): do not hang the GPU
+      bar.state[1] = 1u;
+      break;
+    }
+  }
 }
 
 template <typename T, typename I, typename O>
 int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
                 const void* x, void* y) {
-  if (p->num_tiles == 0)
-    return SPBLAS_B200_SUCCESS;
+  if (p->num_tiles == 0 && p->barrier.n == 0)
+    return SPBLAS_B200_SUCCESS; // (a rank with no rows still takes part in the barrier)
   const T a = *static_cast<const T*>(alpha);
   const auto aligned16 = [](const void* q) {
     return (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
@@ -839,8 +961,35 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
     variant = kVariantMergeTile; // bulk copies need 16-byte aligned arrays
   p->spmv_variant = variant;
 
-  cudaError_t e;
-  if (variant == kVariantPipelined) {
+  ScatterArgs<T> sc;
+  sc.n = p->scatter.n;
+  sc.multicast = p->scatter.multicast;
+  sc.lo_min = INT64_MAX;
+  sc.hi_max = INT64_MIN;
+  for (int d = 0; d < kMaxPeers; ++d) {
+    sc.dst[d] = d < sc.n ? static_cast<T*>(p->scatter.dst[d]) : nullptr;
+    sc.lo[d] = d < sc.n ? p->scatter.lo[d] : 0;
+    sc.hi[d] = d < sc.n ? p->scatter.hi[d] : 0;
+    if (d < sc.n && sc.lo[d] < sc.hi[d]) {
+      sc.lo_min = sc.lo[d] < sc.lo_min ? sc.lo[d] : sc.lo_min;
+      sc.hi_max = sc.hi[d] > sc.hi_max ? sc.hi[d] : sc.hi_max;
+    }
+  }
+  BarrierArgs bar;
+  bar.n = p->barrier.n;
+  bar.epoch = 0;
+  bar.state = static_cast<unsigned int*>(p->barrier_state.p);
+  for (int d = 0; d < kMaxPeers; ++d) {
+    bar.remote[d] = d < bar.n ? p->barrier.remote[d] : nullptr;
+    bar.local[d] = d < bar.n ? p->barrier.local[d] : nullptr;
+  }
+  if (bar.n > 0)
+    bar.epoch = ++p->barrier_epoch;
+
+  cudaError_t e = cudaSuccess;
+  if (p->num_tiles == 0) {
+    // nothing to multiply: only the fix-up kernel's barrier runs
+  } else if (variant == kVariantPipelined) {
     // Pipeline shape: stages x (header + tile data) of shared memory per CTA; shared
     // memory decides how many CTAs fit per SM.
     const int data_bytes = pipe_stage_data_bytes(p->tile_items, sizeof(T), sizeof(I),
@@ -874,7 +1023,7 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
           static_cast<const int64_t*>(p->tile_starts.p),
           static_cast<const int*>(p->tile_uniform.p), p->num_tiles, p->csr_rows, nnz_end,
           static_cast<int64_t*>(p->carry_row.p), static_cast<T*>(p->carry_val.p), stages,
-          data_bytes);
+          data_bytes, sc);
       return cudaGetLastError();
     };
     e = cw == 16 ? launch(spmv_pipe_kernel<T, I, O, 16>, 16 * 32 + 32)
@@ -893,20 +1042,21 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
         static_cast<const T*>(values), static_cast<const O*>(p->csr_perm),
         static_cast<const T*>(x), static_cast<T*>(y), a,
         static_cast<const int64_t*>(p->tile_starts.p), p->csr_rows, nnz_end,
-        static_cast<int64_t*>(p->carry_row.p), static_cast<T*>(p->carry_val.p), vec_ok);
+        static_cast<int64_t*>(p->carry_row.p), static_cast<T*>(p->carry_val.p), vec_ok, sc);
     e = cudaGetLastError();
     if (e != cudaSuccess)
       return cuda_fail(p, e, "spmv_merge_tile_kernel");
   }
-  const unsigned fgrid = unsigned((p->num_tiles + 255) / 256);
+  const unsigned fgrid = p->num_tiles > 0 ? unsigned((p->num_tiles + 255) / 256) : 1u;
   spmv_carry_fixup_kernel<T><<<fgrid, 256, 0, p->stream>>>(
       static_cast<const int64_t*>(p->carry_row.p),
-      static_cast<const T*>(p->carry_val.p), p->num_tiles, static_cast<T*>(y), a);
+      static_cast<const T*>(p->carry_val.p), p->num_tiles, static_cast<T*>(y), a, sc, bar);
   e = cudaGetLastError();
   if (e != cudaSuccess)
     return cuda_fail(p, e, "spmv_carry_fixup_kernel");
-  p->last_launches = 2;
-  p->total_launches += 2;
+  const int launched = p->num_tiles > 0 ? 2 : 1;
+  p->last_launches = launched;
+  p->total_launches += launched;
   return SPBLAS_B200_SUCCESS;
 }
 

@@ -111,6 +111,33 @@ class operation_info_t:
     @property
     def spmm_variant(self): return self._query_scalar(_cabi.Q_SPMM_VARIANT)
 
+    @property
+    def barrier_epoch(self): return self._query_scalar(_cabi.Q_BARRIER_EPOCH)
+    @property
+    def barrier_timeout(self): return self._query_scalar(_cabi.Q_BARRIER_TIMEOUT)
+
+    # -- fused exchange (include/spblas_b200.h: set_scatter / set_barrier) ---------------
+    def set_scatter(self, dsts=(), multicast: bool = False):
+        """dsts: (device address of this block's row 0 in the destination, row_begin, row_end)
+        triples; every following SpMV execute on this plan also stores those rows there."""
+        n = len(dsts)
+        ptrs = (C.c_void_p * max(n, 1))(*[int(d[0]) for d in dsts])
+        lo = (C.c_int64 * max(n, 1))(*[int(d[1]) for d in dsts])
+        hi = (C.c_int64 * max(n, 1))(*[int(d[2]) for d in dsts])
+        st = _cabi.lib().spblas_b200_plan_set_scatter(self._plan, n, ptrs, lo, hi,
+                                                      1 if multicast else 0)
+        _cabi.raise_for_status(st, self._err())
+
+    def set_barrier(self, remote_slots=(), local_slots=()):
+        """remote_slots[q]: address of this rank's flag word on peer q; local_slots[q]: address
+        of the word peer q writes here.  Empty: no barrier."""
+        n = len(remote_slots)
+        assert n == len(local_slots)
+        rs = (C.c_void_p * max(n, 1))(*[int(a) for a in remote_slots])
+        ls = (C.c_void_p * max(n, 1))(*[int(a) for a in local_slots])
+        st = _cabi.lib().spblas_b200_plan_set_barrier(self._plan, n, rs, ls)
+        _cabi.raise_for_status(st, self._err())
+
     def effective_csr(self, off_dtype, idx_dtype):
         """(rowptr, colind, perm) of the row-major structure the kernels run on."""
         return (self._query_array(_cabi.Q_CSR_ROWPTR, off_dtype),

@@ -10,6 +10,15 @@ The inspect phase records the column interval [cmin, cmax] its block touches and
   * "halo":      point-to-point exchange of just the overlap with each peer's row block
                  (banded matrices: 5-point Poisson needs g entries per neighbour), or
   * "allgather": every block to every rank (R-MAT and other unstructured matrices).
+
+On GPUs the exchange is FUSED into the product (`fused=True`, the default when the plan is
+given and NVLink peer memory can be mapped): both x replicas live in symmetric memory
+(torch.distributed._symmetric_memory supplies the allocation and the peer mapping — plumbing),
+the SpMV kernels store every row a peer needs straight into that peer's next-x replica, and
+the carry fix-up kernel ends with the cross-GPU flag barrier (include/spblas_b200.h:
+spblas_b200_plan_set_scatter / _set_barrier).  An iteration is then the same two kernel
+launches as on one GPU and contains no collective call.  The NCCL path below stays as the
+fallback (and is what the gloo CPU tests drive).
 """
 from __future__ import annotations
 
@@ -97,7 +106,8 @@ class ShardedSpMV:
 
     def __init__(self, n: int, blocks: Sequence[Tuple[int, int]], col_range: Tuple[int, int],
                  local_multiply: Callable[[torch.Tensor, torch.Tensor], None],
-                 dtype, device, group=None, halo_fraction: float = 0.5):
+                 dtype, device, group=None, halo_fraction: float = 0.5,
+                 info=None, fused: Optional[bool] = None, multicast: bool = False):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -108,8 +118,55 @@ class ShardedSpMV:
         self.local_multiply = local_multiply
         needs = self._gather_needs(col_range, device)
         self.plan = plan_exchange(self.blocks, needs, self.rank, halo_fraction)
-        self.x = [torch.zeros(n, dtype=dtype, device=device) for _ in range(2)]
         self.cur = 0
+        self.info = info
+        self.fused = False
+        self.fused_error = None
+        want = fused if fused is not None else True
+        if (want and info is not None and self.world > 1 and self.plan.mode != "none"
+                and torch.device(device).type == "cuda"):
+            try:
+                self._setup_fused(n, dtype, device, multicast)
+                self.fused = True
+            except Exception as exc:                 # no peer mapping on this box: NCCL path
+                if fused:
+                    raise
+                self.fused_error = repr(exc)
+        if not self.fused:
+            self.x = [torch.zeros(n, dtype=dtype, device=device) for _ in range(2)]
+
+    # -- fused exchange: symmetric x replicas, peer destinations, flag barrier ----------
+    def _setup_fused(self, n, dtype, device, multicast):
+        import torch.distributed._symmetric_memory as symm
+        grp = self.group if self.group is not None else dist.group.WORLD
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        self.x, self._hdl = [], []
+        for _ in range(2):
+            t = symm.empty(n, dtype=dtype, device=device)
+            t.zero_()
+            self.x.append(t)
+            self._hdl.append(symm.rendezvous(t, grp))
+        flags = symm.empty(self.world, dtype=torch.int64, device=device)
+        flags.zero_()
+        self._flags, self._flags_hdl = flags, symm.rendezvous(flags, grp)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)               # every rank's zeros are in place
+        p = self.plan
+        peers = sorted({q for q, _, _ in p.sends} | {q for q, _, _ in p.recvs})
+        fptr = [int(a) for a in self._flags_hdl.buffer_ptrs]
+        self._remote_slots = [fptr[q] + 8 * self.rank for q in peers]
+        self._local_slots = [fptr[self.rank] + 8 * q for q in peers]
+        self._dsts = []
+        for b in range(2):
+            ptrs = [int(a) for a in self._hdl[b].buffer_ptrs]
+            mc = int(getattr(self._hdl[b], "multicast_ptr", 0) or 0)
+            if multicast and mc and p.mode == "allgather":
+                # one multimem store per row reaches every GPU's replica (this one too)
+                self._dsts.append(([(mc + self.r0 * itemsize, 0, self.r1 - self.r0)], True))
+            else:
+                self._dsts.append(([(ptrs[q] + self.r0 * itemsize, b0 - self.r0, e0 - self.r0)
+                                    for q, b0, e0 in p.sends], False))
+        self.multicast = bool(self._dsts[0][1])
 
     def _gather_needs(self, col_range, device):
         if self.world == 1:
@@ -133,9 +190,17 @@ class ShardedSpMV:
         return self.x[self.cur][self.r0:self.r1]
 
     # -- one product, no communication ---------------------------------------------------
-    def multiply(self) -> torch.Tensor:
+    def multiply(self, exchange: bool = False) -> torch.Tensor:
         nxt = self.x[1 - self.cur]
         y = nxt[self.r0:self.r1]
+        if self.fused:
+            if exchange:
+                dsts, mc = self._dsts[1 - self.cur]
+                self.info.set_scatter(dsts, multicast=mc)
+                self.info.set_barrier(self._remote_slots, self._local_slots)
+            else:
+                self.info.set_scatter(())
+                self.info.set_barrier((), ())
         self.local_multiply(self.x[self.cur], y)
         return y
 
@@ -144,6 +209,9 @@ class ShardedSpMV:
         """Make the rows other ranks produced visible in the next x replica, then flip."""
         nxt = self.x[1 - self.cur]
         p = self.plan
+        if self.fused:
+            self.cur = 1 - self.cur                  # the kernels already did it
+            return
         if p.mode == "allgather":
             sizes = {e - b for (b, e) in p.blocks}
             if len(sizes) == 1 and self.n == self.world * (self.r1 - self.r0):
@@ -172,6 +240,6 @@ class ShardedSpMV:
 
     def step(self) -> torch.Tensor:
         """x <- alpha * A x (one iteration of the y -> x loop)."""
-        y = self.multiply()
+        y = self.multiply(exchange=True)
         self.exchange()
         return y
