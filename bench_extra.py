@@ -5,9 +5,45 @@ the same JSON shape so that profiles/ can hold their roofline numbers too.
 C1 is 92 MB — it fits in the 126 MB L2 — so its timed loop rotates over enough independent
 copies of the operands to exceed 2x L2 (cold-L2 protocol)."""
 import json
+import os
+import sys
 import time
 
 import torch
+
+
+def cusparse_compare(kind, operands, steps, scale=1.0):
+    """ms per product of NVIDIA cuSPARSE — what the reference's NVIDIA backend calls
+    (vendor/cusparse/spmv_impl.hpp:80-84, CUSPARSE_SPMV_ALG_DEFAULT) — on the same operands,
+    same box, same timing loop (scripts/cusparse_comparator.py; comparator only).  `operands`
+    is a list of (m, n, rowptr, colind, values, x_or_B, y_or_C) rotated like the timed loop."""
+    if os.environ.get("SPBLAS_B200_NO_CUSPARSE", "0") == "1":
+        return None
+    try:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+        import cusparse_comparator as cc
+        cs = cc.CuSparse()
+        out = {}
+        algs = {"spmv": (("CUSPARSE_SPMV_ALG_DEFAULT", 0), ("CUSPARSE_SPMV_CSR_ALG2", 3)),
+                "spmm": (("CUSPARSE_SPMM_ALG_DEFAULT", 0), ("CUSPARSE_SPMM_CSR_ALG2", 6))}[kind]
+        for name, alg in algs:
+            runs = []
+            for (m, n, rp, ci, v, xin, yout) in operands:
+                if kind == "spmv":
+                    runs.append(cs.spmv(m, n, rp, ci, v, xin, yout, alpha=scale, alg=alg))
+                else:
+                    runs.append(cs.spmm(m, n, xin.shape[1], rp, ci, v, xin, yout, alpha=scale, alg=alg))
+            state = {"i": 0}
+
+            def run():
+                runs[state["i"] % len(runs)]()
+                state["i"] += 1
+            out[name] = cc.time_ms(run, steps)
+        out["note"] = ("comparator only: workspace preallocated, only cusparseSpMV/SpMM timed; the "
+                       "reference's wrapper also pays bufferSize + cudaMalloc + cudaFree per call")
+        return out
+    except Exception as e:                       # the comparator must never break the bench
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def _bytes_spmv(nnz, m, n, sT, sI=4, sO=4):
@@ -54,6 +90,9 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         name = "C1 uniform random CSR SpMV fp32/int32 m=n=1M, 10 nnz/row, scaled(1.2, a)"
         extra["l2_policy"] = f"rotating over {copies} independent operand sets (cold L2)"
         launches_of = lambda: sum(t[3].total_launches for t in mats)
+        cmp_args = ("spmv", [(m, n, t[0].rowptr, t[0].colind, t[0].values, t[1],
+                              torch.empty_like(t[2])) for t in mats], 1.2)
+        result_of = lambda: mats[0][2]
     elif wl == "c4":
         v, rp, ci, shape = G.rmat_csr(24, 16, seed=24, dtype=torch.float32, device=dev)
         m, n = shape
@@ -74,6 +113,8 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         name = "C4 R-MAT scale 24 (edge factor 16) CSR SpMV fp32/int32"
         extra["l2_policy"] = "inputs larger than L2 (2.3 GB)"
         launches_of = lambda: info.total_launches
+        cmp_args = ("spmv", [(m, n, rp, ci, v, x, torch.empty_like(y))], 1.0)
+        result_of = lambda: y
     else:
         k = 32 if wl == "c3k32" else 128
         m = n = 2_000_000
@@ -91,6 +132,8 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         extra["l2_policy"] = "inputs larger than L2"
         extra["gather_model_bytes"] = nnz * 8 + (m + 1) * 4 + nnz * k * 4 + m * k * 4
         launches_of = lambda: info.total_launches
+        cmp_args = ("spmm", [(m, n, rp, ci, v, B, torch.empty_like(C))], 1.0)
+        result_of = lambda: C
 
     sampler.start()
     l0 = launches_of()
@@ -102,6 +145,18 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
     traffic = ncu_traffic(wl)
     if wl.startswith("c3"):
         extra["spmm_variant"] = info.spmm_variant
+    # same-box vendor comparator (the reference's NVIDIA backend is a cuSPARSE wrapper)
+    cusparse = cusparse_compare(cmp_args[0], cmp_args[1], K, cmp_args[2])
+    if cusparse and "unavailable" not in cusparse:
+        ours, theirs = result_of(), cmp_args[1][0][6]
+        fn(0)                                          # operand set 0 again
+        torch.cuda.synchronize()
+        err = (ours.double() - theirs.double()).abs().max().item()
+        ref = theirs.double().abs().max().item()
+        cusparse["max_abs_diff_vs_ours"] = err
+        cusparse["max_abs_result"] = ref
+        best = min(vv for kk, vv in cusparse.items() if kk.startswith("CUSPARSE_"))
+        cusparse["ours_over_best_cusparse"] = best / ms
     line = {
         "metric": "CSR SpMM GFLOP/s" if wl.startswith("c3") else "CSR SpMV GFLOP/s",
         "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": 1, "steps": K,
@@ -115,7 +170,8 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
                      # what the launch really moved through DRAM (ncu), per second: for the
                      # gather-bound configs THIS is what sits against the HBM peak
                      "dram_gbs_at_ncu_traffic": (traffic / (ms * 1e-3) / 1e9) if traffic else None},
-        "clocks": clocks, "gpu_launches": int(launches - W * (launches // (K + W)) if False else launches),
+        "clocks": clocks, "gpu_launches": int(launches),
+        "cusparse": cusparse,
     }
     print(json.dumps(line), flush=True)
 

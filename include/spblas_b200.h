@@ -156,6 +156,22 @@ SPBLAS_B200_API int spblas_b200_spmv(spblas_b200_plan* plan, int val_type,
                                      const void* alpha, const void* d_values,
                                      const void* d_x, void* d_y);
 
+/* The same product with HOST vectors: h_y[m] = alpha * A * h_x[n].  A (values and the
+   inspected structure) stays on the device; d_x[n] and d_y[m] are device staging
+   buffers the caller provides (nothing is allocated here).  The upload of x, the
+   kernels and the download of y are pipelined chunk by chunk over the plan's tiles:
+   chunk c is multiplied as soon as the part of x its columns reach has arrived, and
+   its rows travel back while later chunks are multiplied — for a banded matrix PCIe
+   is busy in both directions for the whole call.  Bit-identical to spblas_b200_spmv.
+   Pinned (page-locked) host memory is needed for the copies to be asynchronous.
+   The call is complete in the order of the plan's stream: synchronise that stream
+   (or the device) before reading h_y.  No reference counterpart: the reference's GPU
+   backends take device pointers only (vendor/cusparse/spmv_impl.hpp:50-66). */
+SPBLAS_B200_API int spblas_b200_spmv_host(spblas_b200_plan* plan, int val_type,
+                                          const void* alpha, const void* d_values,
+                                          const void* h_x, void* h_y, void* d_x,
+                                          void* d_y);
+
 /* C[m x k] = alpha * A * B[n x k], B and C row-major with leading dimensions
    ldb, ldc (>= k) in elements. */
 SPBLAS_B200_API int spblas_b200_spmm(spblas_b200_plan* plan, int val_type,

@@ -8,12 +8,14 @@ the host-side mirror of the same interface used by the tests and the benchmark; 
 no compute and no CPU fallback.
 """
 from . import _cabi
-from .multiply import multiply, multiply_execute, multiply_inspect, operation_info_t
+from .multiply import (multiply, multiply_execute, multiply_execute_host, multiply_inspect,
+                       operation_info_t)
 from .views import (conjugated, csc_view, csr_view, matrix_opt, scaled, scaled_view,
                     transposed)
 
 __all__ = [
-    "multiply", "multiply_inspect", "multiply_execute", "operation_info_t",
+    "multiply", "multiply_inspect", "multiply_execute", "multiply_execute_host",
+    "operation_info_t",
     "csr_view", "csc_view", "scaled", "scaled_view", "transposed", "matrix_opt",
     "conjugated",
 ]

@@ -67,6 +67,8 @@ void release_all(spblas_b200_plan* p) {
                           &p->spmm_carry_row, &p->spmm_carry_val, &p->barrier_state};
   for (DeviceBuffer* b : bufs)
     release(*b);
+  release(p->hc_colmax);
+  release_host_exec(p);
 }
 
 bool valid_index_type(int t) { return t == SPBLAS_B200_I32 || t == SPBLAS_B200_I64; }
@@ -153,6 +155,8 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->ctas_per_sm = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_CONSUMER_WARPS"))
     p->consumer_warps = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_HOST_CHUNKS"))
+    p->host_chunks_override = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_SPMM_VARIANT"))
     p->spmm_forced = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_SPMM_CTAS_PER_SM"))
@@ -243,6 +247,7 @@ int spblas_b200_inspect(spblas_b200_plan* p, int format, int64_t m, int64_t n,
     return SPBLAS_B200_INVALID_ARGUMENT;
   p->err.clear();
   p->inspected = false;
+  p->host_chunks = 0; // the chunk table belongs to the previous structure
   if (format != SPBLAS_B200_CSR && format != SPBLAS_B200_CSC)
     return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "format must be CSR or CSC");
   if (!valid_index_type(off_type) || !valid_index_type(idx_type))
@@ -293,6 +298,24 @@ int spblas_b200_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
       (p->m > 0 && !d_y))
     return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null device pointer");
   return run_spmv(p, val_type, alpha, d_values, d_x, d_y);
+}
+
+int spblas_b200_spmv_host(spblas_b200_plan* p, int val_type, const void* alpha,
+                          const void* d_values, const void* h_x, void* h_y,
+                          void* d_x, void* d_y) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  if (!p->inspected)
+    return fail(p, SPBLAS_B200_NOT_INSPECTED, "spmv_host called before inspect");
+  if (!valid_value_type(val_type))
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "value type must be f32, f64 or s32");
+  if (!alpha)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "alpha is null");
+  if ((p->nnz > 0 && !d_values) || (p->n > 0 && p->nnz > 0 && (!h_x || !d_x)) ||
+      (p->m > 0 && (!h_y || !d_y)))
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null pointer");
+  return run_spmv_host(p, val_type, alpha, d_values, h_x, h_y, d_x, d_y);
 }
 
 int spblas_b200_spmm(spblas_b200_plan* p, int val_type, const void* alpha,

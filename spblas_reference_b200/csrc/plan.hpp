@@ -12,6 +12,7 @@
 
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "../../include/spblas_b200.h"
 
@@ -137,6 +138,19 @@ struct spblas_b200_plan {
   unsigned long long barrier_epoch = 0; // steps signalled so far
   b200::DeviceBuffer barrier_state;     // uint32 block counter, uint32 timeout flag
 
+  // ---- host-buffer execute (spblas_b200_spmv_host, host_exec.cu) -----------------
+  // The tiles cut into `host_chunks` consecutive chunks; chunk c covers tiles
+  // [hc_tile[c], hc_tile[c+1]), completes rows [hc_row[c], hc_row[c+1]) and reads
+  // x[0 .. hc_xneed[c]) at most (running maximum of the columns referenced so far), so
+  // the upload of x, the products and the download of y overlap chunk by chunk.
+  int host_chunks = 0; // 0: table not built for the current structure
+  std::vector<int64_t> hc_tile, hc_row, hc_xneed;
+  int64_t hc_xlo = 0; // smallest column referenced: x below it is never uploaded
+  b200::DeviceBuffer hc_colmax; // int64 per chunk (device scratch of the table build)
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  std::vector<cudaEvent_t> hc_events; // 2 per chunk + 2
+  int host_chunks_override = 0;       // env SPBLAS_B200_HOST_CHUNKS
+
   int forced_variant = -1;
   int spmv_variant = b200::kVariantMergeTile;
   int spmm_variant = 0;
@@ -167,6 +181,14 @@ int build_stream_partition(spblas_b200_plan* p, int64_t streams);
 // spmv.cu
 int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
              const void* values, const void* x, void* y);
+int run_spmv_tiles(spblas_b200_plan* p, int val_type, const void* alpha,
+                   const void* values, const void* x, void* y, int64_t tile_begin,
+                   int64_t tile_end);
+// host_exec.cu
+int run_spmv_host(spblas_b200_plan* p, int val_type, const void* alpha,
+                  const void* values, const void* h_x, void* h_y, void* d_x,
+                  void* d_y);
+void release_host_exec(spblas_b200_plan* p);
 // spmm.cu
 int run_spmm(spblas_b200_plan* p, int val_type, const void* alpha,
              const void* values, const void* B, int64_t ldb, void* C,

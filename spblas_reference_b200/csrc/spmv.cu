@@ -368,8 +368,8 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
                  const T* __restrict__ values, const O* __restrict__ perm,
                  const T* __restrict__ x, T* __restrict__ y, const T alpha,
                  const int64_t* __restrict__ tile_starts,
-                 const int* __restrict__ tile_uniform, const int64_t num_tiles,
-                 const int64_t rows, const int64_t nnz_end,
+                 const int* __restrict__ tile_uniform, const int64_t tile_first,
+                 const int64_t num_tiles, const int64_t rows, const int64_t nnz_end,
                  int64_t* __restrict__ carry_row, T* __restrict__ carry_val,
                  const int stages, const int stage_data_bytes,
                  const __grid_constant__ ScatterArgs<T> sc) {
@@ -387,9 +387,9 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
   const int warp = tid >> 5;
   const bool has_perm = perm != nullptr;
 
-  // contiguous run of tiles for this CTA
-  const int64_t t_begin = num_tiles * int64_t(blockIdx.x) / gridDim.x;
-  const int64_t t_end = num_tiles * int64_t(blockIdx.x + 1) / gridDim.x;
+  // contiguous run of tiles for this CTA out of [tile_first, tile_first + num_tiles)
+  const int64_t t_begin = tile_first + num_tiles * int64_t(blockIdx.x) / gridDim.x;
+  const int64_t t_end = tile_first + num_tiles * int64_t(blockIdx.x + 1) / gridDim.x;
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -692,8 +692,8 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
                        const O* __restrict__ perm, const T* __restrict__ x,
                        T* __restrict__ y, const T alpha,
                        const int64_t* __restrict__ tile_starts,
-                       const int64_t rows, const int64_t nnz_end,
-                       int64_t* __restrict__ carry_row,
+                       const int64_t tile_first, const int64_t rows,
+                       const int64_t nnz_end, int64_t* __restrict__ carry_row,
                        T* __restrict__ carry_val, const int vec_ok,
                        const __grid_constant__ ScatterArgs<T> sc) {
   constexpr int THREADS = kSpmvThreads;
@@ -710,7 +710,7 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int64_t t = blockIdx.x;
+  const int64_t t = tile_first + blockIdx.x;
   const int64_t row0 = tile_starts[2 * t], k0 = tile_starts[2 * t + 1];
   const int64_t row1 = tile_starts[2 * t + 2], k1 = tile_starts[2 * t + 3];
   const int nr = int(row1 - row0);
@@ -872,7 +872,10 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
 
 // Adds the carries of tiles that ended inside a row to that row's y.  A run of
 // consecutive tiles carrying into the same row (a row spanning several tiles) is
-// summed in tile order by the thread of the run's first tile.
+// summed in tile order by the thread of the run's LAST tile — the row itself ends in
+// the tile after it, so a launch over tiles [fix_lo, fix_hi) completes exactly the
+// rows that end in tiles [fix_lo + 1, fix_hi + 1): a chunk of tiles can be finished
+// (and its rows shipped to the host) before later chunks have run.
 //
 // With a fused exchange this kernel is also where the iteration's cross-GPU barrier
 // lives: the last CTA to finish tells every peer "my rows of step `epoch` are in your
@@ -882,16 +885,19 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
 template <typename T>
 __global__ void __launch_bounds__(256)
 spmv_carry_fixup_kernel(const int64_t* __restrict__ carry_row,
-                        const T* __restrict__ carry_val, int64_t num_tiles,
-                        T* __restrict__ y, const T alpha,
-                        const __grid_constant__ ScatterArgs<T> sc,
+                        const T* __restrict__ carry_val, int64_t fix_lo,
+                        int64_t fix_hi, int64_t num_tiles, T* __restrict__ y,
+                        const T alpha, const __grid_constant__ ScatterArgs<T> sc,
                         const __grid_constant__ BarrierArgs bar) {
-  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t < num_tiles) {
+  const int64_t t = fix_lo + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t < fix_hi) {
     const int64_t r = carry_row[t];
-    if (r >= 0 && !(t > 0 && carry_row[t - 1] == r)) {
-      T sum = carry_val[t];
-      for (int64_t j = t + 1; j < num_tiles && carry_row[j] == r; ++j)
+    if (r >= 0 && !(t + 1 < num_tiles && carry_row[t + 1] == r)) {
+      int64_t s = t;
+      while (s > 0 && carry_row[s - 1] == r)
+        --s;
+      T sum = carry_val[s];
+      for (int64_t j = s + 1; j <= t; ++j)
         sum += carry_val[j];
       const T v = y[r] + alpha * sum;
       y[r] = v;
@@ -933,11 +939,15 @@ spmv_carry_fixup_kernel(const int64_t* __restrict__ carry_row,
   }
 }
 
+// Tiles [T0, T1) of the partition (the whole product: [0, num_tiles)).  A proper
+// sub-range is one chunk of a host-buffer execute (host_exec.cu): chunks are launched
+// in ascending order on one stream, and each completes the rows that end in its tiles.
 template <typename T, typename I, typename O>
 int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
-                const void* x, void* y) {
+                const void* x, void* y, int64_t T0, int64_t T1) {
   if (p->num_tiles == 0 && p->barrier.n == 0)
     return SPBLAS_B200_SUCCESS; // (a rank with no rows still takes part in the barrier)
+  const int64_t ntiles = T1 - T0;
   const T a = *static_cast<const T*>(alpha);
   const auto aligned16 = [](const void* q) {
     return (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
@@ -987,7 +997,7 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
     bar.epoch = ++p->barrier_epoch;
 
   cudaError_t e = cudaSuccess;
-  if (p->num_tiles == 0) {
+  if (ntiles <= 0) {
     // nothing to multiply: only the fix-up kernel's barrier runs
   } else if (variant == kVariantPipelined) {
     // Pipeline shape: stages x (header + tile data) of shared memory per CTA; shared
@@ -1009,8 +1019,8 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
     const size_t smem = 128 + size_t(stages) * per_stage;
     const int cw = p->consumer_warps == 16 ? 16 : 8;
     int64_t grid = int64_t(p->num_sms) * ctas_per_sm;
-    if (grid > p->num_tiles)
-      grid = p->num_tiles;
+    if (grid > ntiles)
+      grid = ntiles;
     auto launch = [&](auto kern, int threads) -> cudaError_t {
       cudaError_t e2 = cudaFuncSetAttribute(
           kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
@@ -1021,7 +1031,7 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
           static_cast<const T*>(values), static_cast<const O*>(p->csr_perm),
           static_cast<const T*>(x), static_cast<T*>(y), a,
           static_cast<const int64_t*>(p->tile_starts.p),
-          static_cast<const int*>(p->tile_uniform.p), p->num_tiles, p->csr_rows, nnz_end,
+          static_cast<const int*>(p->tile_uniform.p), T0, ntiles, p->csr_rows, nnz_end,
           static_cast<int64_t*>(p->carry_row.p), static_cast<T*>(p->carry_val.p), stages,
           data_bytes, sc);
       return cudaGetLastError();
@@ -1037,58 +1047,72 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess)
       return cuda_fail(p, e, "cudaFuncSetAttribute(spmv_merge_tile_kernel)");
-    kern<<<unsigned(p->num_tiles), kSpmvThreads, smem, p->stream>>>(
+    kern<<<unsigned(ntiles), kSpmvThreads, smem, p->stream>>>(
         static_cast<const O*>(p->csr_rowptr), static_cast<const I*>(p->csr_colind),
         static_cast<const T*>(values), static_cast<const O*>(p->csr_perm),
         static_cast<const T*>(x), static_cast<T*>(y), a,
-        static_cast<const int64_t*>(p->tile_starts.p), p->csr_rows, nnz_end,
+        static_cast<const int64_t*>(p->tile_starts.p), T0, p->csr_rows, nnz_end,
         static_cast<int64_t*>(p->carry_row.p), static_cast<T*>(p->carry_val.p), vec_ok, sc);
     e = cudaGetLastError();
     if (e != cudaSuccess)
       return cuda_fail(p, e, "spmv_merge_tile_kernel");
   }
-  const unsigned fgrid = p->num_tiles > 0 ? unsigned((p->num_tiles + 255) / 256) : 1u;
-  spmv_carry_fixup_kernel<T><<<fgrid, 256, 0, p->stream>>>(
-      static_cast<const int64_t*>(p->carry_row.p),
-      static_cast<const T*>(p->carry_val.p), p->num_tiles, static_cast<T*>(y), a, sc, bar);
-  e = cudaGetLastError();
-  if (e != cudaSuccess)
-    return cuda_fail(p, e, "spmv_carry_fixup_kernel");
-  const int launched = p->num_tiles > 0 ? 2 : 1;
-  p->last_launches = launched;
+  // carries whose row ends inside [T0, T1): runs whose last tile is in [T0 - 1, T1 - 1)
+  // (the partition's last tile never carries, so the final chunk simply runs to T1)
+  const int64_t fix_lo = T0 > 0 ? T0 - 1 : 0;
+  const int64_t fix_hi = T1 >= p->num_tiles ? p->num_tiles : T1 - 1;
+  const int64_t fix_n = fix_hi > fix_lo ? fix_hi - fix_lo : 0;
+  const unsigned fgrid = fix_n > 0 ? unsigned((fix_n + 255) / 256) : 1u;
+  if (fix_n > 0 || bar.n > 0) {
+    spmv_carry_fixup_kernel<T><<<fgrid, 256, 0, p->stream>>>(
+        static_cast<const int64_t*>(p->carry_row.p),
+        static_cast<const T*>(p->carry_val.p), fix_lo, fix_hi, p->num_tiles,
+        static_cast<T*>(y), a, sc, bar);
+    e = cudaGetLastError();
+    if (e != cudaSuccess)
+      return cuda_fail(p, e, "spmv_carry_fixup_kernel");
+  }
+  const int launched = (ntiles > 0 ? 1 : 0) + ((fix_n > 0 || bar.n > 0) ? 1 : 0);
+  p->last_launches += launched;
   p->total_launches += launched;
   return SPBLAS_B200_SUCCESS;
 }
 
 template <typename T>
 int dispatch_index(spblas_b200_plan* p, const void* alpha, const void* values,
-                   const void* x, void* y) {
+                   const void* x, void* y, int64_t T0, int64_t T1) {
   const bool i64 = p->idx_type == SPBLAS_B200_I64;
   const bool o64 = p->off_type == SPBLAS_B200_I64;
   if (!i64 && !o64)
-    return launch_spmv<T, int32_t, int32_t>(p, alpha, values, x, y);
+    return launch_spmv<T, int32_t, int32_t>(p, alpha, values, x, y, T0, T1);
   if (!i64 && o64)
-    return launch_spmv<T, int32_t, int64_t>(p, alpha, values, x, y);
+    return launch_spmv<T, int32_t, int64_t>(p, alpha, values, x, y, T0, T1);
   if (i64 && !o64)
-    return launch_spmv<T, int64_t, int32_t>(p, alpha, values, x, y);
-  return launch_spmv<T, int64_t, int64_t>(p, alpha, values, x, y);
+    return launch_spmv<T, int64_t, int32_t>(p, alpha, values, x, y, T0, T1);
+  return launch_spmv<T, int64_t, int64_t>(p, alpha, values, x, y, T0, T1);
 }
 
 } // namespace
 
-int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
-             const void* values, const void* x, void* y) {
-  p->last_launches = 0;
+int run_spmv_tiles(spblas_b200_plan* p, int val_type, const void* alpha,
+                   const void* values, const void* x, void* y, int64_t T0,
+                   int64_t T1) {
   switch (val_type) {
   case SPBLAS_B200_F32:
-    return dispatch_index<float>(p, alpha, values, x, y);
+    return dispatch_index<float>(p, alpha, values, x, y, T0, T1);
   case SPBLAS_B200_F64:
-    return dispatch_index<double>(p, alpha, values, x, y);
+    return dispatch_index<double>(p, alpha, values, x, y, T0, T1);
   case SPBLAS_B200_S32:
-    return dispatch_index<int32_t>(p, alpha, values, x, y);
+    return dispatch_index<int32_t>(p, alpha, values, x, y, T0, T1);
   default:
     return fail(p, SPBLAS_B200_NOT_SUPPORTED, "unknown value type");
   }
+}
+
+int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
+             const void* values, const void* x, void* y) {
+  p->last_launches = 0;
+  return run_spmv_tiles(p, val_type, alpha, values, x, y, 0, p->num_tiles);
 }
 
 } // namespace b200

@@ -301,3 +301,47 @@ def multiply_execute(info: operation_info_t, a, x, y):
     if not isinstance(info, operation_info_t):
         raise TypeError("multiply_execute(info, a, x, y)")
     return _execute(info, a, x, y)
+
+
+def multiply_execute_host(info: operation_info_t, a, x_host: torch.Tensor, y_host: torch.Tensor):
+    """y_host = alpha * A * x_host for HOST vectors (pinned memory for asynchronous copies);
+    A and the inspected plan stay on the device.  One C-ABI call (spblas_b200_spmv_host)
+    that pipelines upload, kernels and download chunk by chunk over the plan's tiles
+    (csrc/host_exec.cu); bit-identical to multiply_execute on device vectors.  Complete in
+    the order of the current stream: synchronise before reading y_host.  The device staging
+    vectors are owned by `info` and reused."""
+    if not isinstance(info, operation_info_t):
+        raise TypeError("multiply_execute_host(info, a, x_host, y_host)")
+    a_base, fmt, ptr, ind = _decode_matrix(a)
+    if is_conjugated(x_host) or is_conjugated(y_host):
+        raise RuntimeError("b200 backend does not support conjugated views.")
+    x_base = get_ultimate_base(x_host)
+    if not isinstance(y_host, torch.Tensor) or _is_matrix(y_host):
+        raise TypeError("multiply_execute_host: SpMV only, plain 1-D host tensors")
+    _check_shapes(a_base, x_base, y_host)
+    for t, what in ((x_base, "x_host"), (y_host, "y_host")):
+        if t.is_cuda or not t.is_contiguous():
+            raise RuntimeError(f"{what} must be a contiguous host tensor")
+    vt = value_type(a_base.values)
+    if x_base.dtype != a_base.values.dtype or y_host.dtype != a_base.values.dtype:
+        raise RuntimeError("b200 backend needs A, x and y of one scalar type")
+    alpha = get_scaling_factor(a, x_host)
+    alpha_np = np.array([1 if alpha is None else alpha], dtype=_NP[vt])
+    dev = a_base.values.device
+    m, n = a_base.shape
+    with torch.cuda.device(dev):
+        if info._sig != _signature(fmt, a_base, ptr, ind):
+            _inspect(info, a, torch.empty(n, dtype=x_base.dtype, device=dev),
+                     torch.empty(m, dtype=x_base.dtype, device=dev))
+        stage = getattr(info, "_stage", None)
+        if stage is None or stage[0].dtype != x_base.dtype or stage[0].numel() < n \
+                or stage[1].numel() < m:
+            stage = (torch.empty(max(n, 1), dtype=x_base.dtype, device=dev),
+                     torch.empty(max(m, 1), dtype=x_base.dtype, device=dev))
+            info._stage = stage
+        L = _cabi.lib()
+        L.spblas_b200_plan_set_stream(info._plan, _stream_ptr(dev))
+        st = L.spblas_b200_spmv_host(info._plan, vt, alpha_np.ctypes.data_as(C.c_void_p),
+                                     a_base.values.data_ptr(), x_base.data_ptr(),
+                                     y_host.data_ptr(), stage[0].data_ptr(), stage[1].data_ptr())
+    _cabi.raise_for_status(st, info._err())
