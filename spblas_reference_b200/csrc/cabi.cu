@@ -64,7 +64,8 @@ void release_all(spblas_b200_plan* p) {
                           &p->sort_ws,     &p->tile_starts, &p->tile_uniform, &p->carry_row,
                           &p->carry_val,   &p->segments,   &p->seg_partial,
                           &p->seg_counter, &p->stats,      &p->spmm_starts,
-                          &p->spmm_carry_row, &p->spmm_carry_val, &p->barrier_state};
+                          &p->spmm_carry_row, &p->spmm_carry_val, &p->barrier_state,
+                          &p->ws_starts, &p->ws_carry_row, &p->ws_carry_val};
   for (DeviceBuffer* b : bufs)
     release(*b);
   release(p->hc_colmax);
@@ -155,6 +156,8 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->ctas_per_sm = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_CONSUMER_WARPS"))
     p->consumer_warps = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_WS_ITEMS"))
+    p->ws_items_override = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_HOST_CHUNKS"))
     p->host_chunks_override = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_SPMM_VARIANT"))

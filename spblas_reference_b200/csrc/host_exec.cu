@@ -54,15 +54,15 @@ chunk_colmax_kernel(const I* __restrict__ colind, const int64_t* __restrict__ ti
   }
 }
 
-int build_chunks(spblas_b200_plan* p) {
+int build_chunks(spblas_b200_plan* p, const int64_t* ts, int64_t units) {
   int chunks = p->host_chunks_override > 0 ? p->host_chunks_override : 16;
-  chunks = std::min<int64_t>(std::min(chunks, kMaxHostChunks), std::max<int64_t>(p->num_tiles, 1));
+  chunks = std::min<int64_t>(std::min(chunks, kMaxHostChunks), std::max<int64_t>(units, 1));
   p->hc_tile.assign(chunks + 1, 0);
   p->hc_row.assign(chunks + 1, 0);
   p->hc_xneed.assign(chunks, 0);
   for (int c = 0; c <= chunks; ++c)
-    p->hc_tile[c] = p->num_tiles * c / chunks;
-  if (p->num_tiles == 0) {
+    p->hc_tile[c] = units * c / chunks;
+  if (units == 0) {
     p->hc_row[chunks] = p->csr_rows;
     p->host_chunks = chunks;
     return SPBLAS_B200_SUCCESS;
@@ -80,7 +80,6 @@ int build_chunks(spblas_b200_plan* p) {
   B200_CUDA_TRY(p, cudaMemcpyAsync(d_max + chunks, &huge, sizeof(huge), cudaMemcpyHostToDevice,
                                    p->stream));
   const dim3 grid(chunks, 64);
-  const int64_t* ts = static_cast<const int64_t*>(p->tile_starts.p);
   if (p->idx_type == SPBLAS_B200_I64)
     chunk_colmax_kernel<int64_t><<<grid, 256, 0, p->stream>>>(
         static_cast<const int64_t*>(p->csr_colind), ts, d_tile, d_max);
@@ -140,13 +139,22 @@ int run_spmv_host(spblas_b200_plan* p, int val_type, const void* alpha,
   if (p->scatter.n > 0 || p->barrier.n > 0)
     return fail(p, SPBLAS_B200_NOT_SUPPORTED,
                 "host-buffer execute on a plan with a fused exchange");
-  if (p->host_chunks == 0)
-    if (int rc = build_chunks(p))
+  // the chunks are cut at units of the partition the chosen kernel runs on (tiles, or
+  // warp streams), so every unit is processed exactly as in a device-vector execute
+  int variant = 0;
+  const int64_t* starts = nullptr;
+  int64_t units = 0;
+  if (int rc = prepare_spmv(p, val_type, values, &variant, &starts, &units))
+    return rc;
+  if (p->host_chunks == 0 || p->hc_variant != variant) {
+    if (int rc = build_chunks(p, starts, units))
       return rc;
+    p->hc_variant = variant;
+  }
   const int chunks = p->host_chunks;
   const size_t sT = type_size_val(val_type);
   p->last_launches = 0;
-  if (p->num_tiles == 0) {
+  if (units == 0) {
     // no rows end anywhere: y (if any) is all zeros
     if (p->csr_rows > 0)
       std::memset(h_y, 0, size_t(p->csr_rows) * sT);

@@ -545,7 +545,49 @@ int stream_partition_typed(spblas_b200_plan* p, int64_t streams) {
   return SPBLAS_B200_SUCCESS;
 }
 
+template <typename O>
+int ws_partition_typed(spblas_b200_plan* p, int items, int64_t streams) {
+  if (int rc = reserve(p, p->ws_starts, size_t(streams + 1) * 2 * sizeof(int64_t)))
+    return rc;
+  if (int rc = reserve(p, p->ws_carry_row, size_t(streams) * sizeof(int64_t)))
+    return rc;
+  if (int rc = reserve(p, p->ws_carry_val, size_t(streams) * 8))
+    return rc;
+  const int grid = int((streams + 1 + 255) / 256);
+  merge_partition_kernel<O><<<grid, 256, 0, p->stream>>>(
+      static_cast<const O*>(p->csr_rowptr), p->csr_rows, p->nnz, p->base, items, streams,
+      static_cast<int64_t*>(p->ws_starts.p));
+  if (int e = launch_ok(p, "merge_partition_kernel (SpMV warp streams)"))
+    return e;
+  p->ws_streams = streams;
+  p->ws_items = items;
+  return SPBLAS_B200_SUCCESS;
+}
+
 } // namespace
+
+// The warp-stream table of spmv_warp_stream_kernel: the merged sequence cut into runs
+// of `items` merge items, one run per resident warp when the matrix is small, runs of
+// 4096 items dealt round-robin to the warps when it is large.
+int build_ws_partition(spblas_b200_plan* p, int64_t resident_warps) {
+  const int64_t total = p->csr_rows + p->nnz;
+  int64_t items = (total + resident_warps - 1) / resident_warps;
+  if (p->ws_items_override > 0)
+    items = p->ws_items_override;
+  else if (items > 4096)
+    items = 4096;
+  if (items < 256)
+    items = 256;
+  const int64_t streams = total > 0 ? (total + items - 1) / items : 0;
+  if (streams > int64_t(0x7fffffff))
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "too many warp streams");
+  if (streams == 0) {
+    p->ws_streams = 0;
+    return SPBLAS_B200_SUCCESS;
+  }
+  return p->off_type == SPBLAS_B200_I64 ? ws_partition_typed<int64_t>(p, int(items), streams)
+                                        : ws_partition_typed<int32_t>(p, int(items), streams);
+}
 
 // The SpMM stream table: the same merge-path cut as the SpMV tiles, but into exactly
 // `streams` runs (one per resident warp of spmm_ring_kernel).
@@ -558,7 +600,8 @@ int inspect_structure(spblas_b200_plan* p, int flags) {
   const bool i64 = p->idx_type == SPBLAS_B200_I64;
   const bool o64 = p->off_type == SPBLAS_B200_I64;
   int rc;
-  p->spmm_streams = 0; // the stream table belongs to the previous structure
+  p->spmm_streams = 0; // the stream tables belong to the previous structure
+  p->ws_streams = -1;
   if (!i64 && !o64)
     rc = inspect_typed<int32_t, int32_t>(p, flags);
   else if (!i64 && o64)

@@ -39,6 +39,10 @@ enum SpmvVariant : int {
   // and cp.async of the row ends into a multi-stage shared-memory ring, one
   // producer warp + 8 consumer warps that reduce rows straight out of the ring.
   kVariantPipelined = 1,
+  // autonomous warps over warp-granular merge-path streams, 256 nonzeros per step,
+  // rows reduced out of a per-warp slab with __syncwarp() only: the general path for
+  // matrices bound by random gathers of x (needs 16-byte aligned colind/values).
+  kVariantWarpStream = 2,
 };
 
 struct DeviceBuffer {
@@ -125,6 +129,14 @@ struct spblas_b200_plan {
   int spmm_ctas_per_sm = 0;          // env SPBLAS_B200_SPMM_CTAS_PER_SM (0 = what fits)
   float spmm_l2_fraction = -1.f;     // env SPBLAS_B200_SPMM_L2FRAC: share of B kept evict_last (<0: auto)
 
+  // ---- SpMV warp streams (spmv_warp_stream_kernel) ----------------------------------
+  int64_t ws_streams = -1;         // -1: table not built for the current structure
+  int ws_items = 0;                // merge items per stream
+  int ws_items_override = 0;       // env SPBLAS_B200_WS_ITEMS (tuning)
+  b200::DeviceBuffer ws_starts;    // int64 (row, nnz) pairs, ws_streams + 1 entries
+  b200::DeviceBuffer ws_carry_row; // int64 per stream
+  b200::DeviceBuffer ws_carry_val; // 8 bytes per stream
+
   // ---- statistics -------------------------------------------------------------
   bool have_hist = false;
   int64_t hist[SPBLAS_B200_HIST_BINS] = {0};
@@ -144,6 +156,7 @@ struct spblas_b200_plan {
   // x[0 .. hc_xneed[c]) at most (running maximum of the columns referenced so far), so
   // the upload of x, the products and the download of y overlap chunk by chunk.
   int host_chunks = 0; // 0: table not built for the current structure
+  int hc_variant = -1; // the kernel variant (hence partition) the table was cut for
   std::vector<int64_t> hc_tile, hc_row, hc_xneed;
   int64_t hc_xlo = 0; // smallest column referenced: x below it is never uploaded
   b200::DeviceBuffer hc_colmax; // int64 per chunk (device scratch of the table build)
@@ -178,12 +191,17 @@ void release(DeviceBuffer& b);
 // inspect.cu
 int inspect_structure(spblas_b200_plan* p, int flags);
 int build_stream_partition(spblas_b200_plan* p, int64_t streams);
+int build_ws_partition(spblas_b200_plan* p, int64_t resident_warps);
 // spmv.cu
 int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
              const void* values, const void* x, void* y);
 int run_spmv_tiles(spblas_b200_plan* p, int val_type, const void* alpha,
                    const void* values, const void* x, void* y, int64_t tile_begin,
                    int64_t tile_end);
+// the kernel variant this product will use and the partition it runs on (tiles, or warp
+// streams); builds the warp-stream table on first use
+int prepare_spmv(spblas_b200_plan* p, int val_type, const void* values, int* variant,
+                 const int64_t** starts, int64_t* units);
 // host_exec.cu
 int run_spmv_host(spblas_b200_plan* p, int val_type, const void* alpha,
                   const void* values, const void* h_x, void* h_y, void* d_x,

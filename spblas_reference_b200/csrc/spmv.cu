@@ -40,6 +40,16 @@
 
 namespace b200 {
 
+// 128-bit loads and bulk copies need 16-byte aligned colind / values (/ permutation)
+static inline int spmv_vec_ok(const spblas_b200_plan* p, const void* values) {
+  const auto aligned16 = [](const void* q) {
+    return (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
+  };
+  const bool perm = p->csr_perm != nullptr;
+  return aligned16(p->csr_colind) && (perm || aligned16(values)) &&
+         (!perm || aligned16(p->csr_perm));
+}
+
 namespace {
 
 template <typename T>
@@ -682,6 +692,206 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
 }
 
 // ============================================================================
+// Warp-stream kernel: the general path for matrices bound by random gathers of x
+// ============================================================================
+// Such matrices (uniform random columns, R-MAT) are limited by the L1 tag stage —
+// every gathered element of x is its own 128-byte line, one tag lookup per cycle per
+// SM — so the kernel's only job is to keep gathers issuing at all times.  CTA-wide
+// phases (load, barrier, reduce) leave that stage idle between phases; here every
+// WARP is autonomous: it owns whole streams of the merged sequence (row ends ++
+// nonzeros; a second, warp-granular merge-path table built by the inspect code),
+// walks a stream in chunks of 256 nonzeros (two 128-bit loads of colind and of values
+// per lane, eight gathers in flight per lane), and reduces the rows that end inside
+// the chunk out of its own 256-entry slab of shared memory — one lane per row in
+// storage order (the reference's order), the whole warp for rows longer than 32 — with
+// nothing but __syncwarp().  A chunk in which no row ends (the inside of a hub row)
+// never touches shared memory: the lanes' products go straight into a shuffle
+// reduction.  Streams are dealt round-robin (warp w takes streams w, w + W, ...), so
+// every warp samples the whole matrix and the load balances without atomics.  The
+// stream's trailing partial row is a carry, added by the same fix-up kernel.
+constexpr int kWsChunk = 256;   // nonzeros per warp step
+constexpr int kWsWarps = 8;     // warps per CTA
+constexpr int kWsCtasPerSm = 6; // 48 warps per SM (40 with 8-byte values or indices)
+
+template <typename T, typename I>
+constexpr int ws_ctas_per_sm() {
+  return (sizeof(T) == 8 || sizeof(I) == 8) ? kWsCtasPerSm - 1 : kWsCtasPerSm;
+}
+
+template <typename T, typename I, typename O>
+__global__ void __launch_bounds__(kWsWarps * 32, ws_ctas_per_sm<T, I>())
+spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
+                        const T* __restrict__ values, const O* __restrict__ perm,
+                        const T* __restrict__ x, T* __restrict__ y, const T alpha,
+                        const int64_t* __restrict__ starts, const int64_t stream_first,
+                        const int64_t num_streams, const int64_t rows,
+                        const int64_t nnz_end,
+                        int64_t* __restrict__ carry_row, T* __restrict__ carry_val,
+                        const __grid_constant__ ScatterArgs<T> sc) {
+  __shared__ __align__(16) T s_slab[kWsWarps][kWsChunk];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  T* slab = s_slab[warp];
+  const int64_t gw = int64_t(blockIdx.x) * kWsWarps + warp;
+  const int64_t nw = int64_t(gridDim.x) * kWsWarps;
+  const bool has_perm = perm != nullptr;
+
+  for (int64_t s = stream_first + gw; s < stream_first + num_streams; s += nw) {
+    int64_t row = starts[2 * s];
+    const int64_t k_s = starts[2 * s + 1];
+    const int64_t row_e = starts[2 * s + 2];
+    const bool scat = sc.n > 0 && row < sc.hi_max && row_e > sc.lo_min;
+    auto put = [&](int64_t r, T v) {
+      y[r] = v;
+      if (scat)
+        scatter_store(sc, r, v);
+    };
+    // positions inside the stream are ints relative to `base`, the 16-byte aligned
+    // origin of the first chunk
+    const int64_t base = k_s & ~int64_t(3);
+    const I* __restrict__ ci = colind + base;
+    const T* __restrict__ va = values + base;
+    const int k_e = int(starts[2 * s + 3] - base);
+    const int64_t left = nnz_end - base;
+    const int arr_end = left < int64_t(0x7fffffff) ? int(left) : 0x7fffffff;
+    int rows_left = int(row_e - row);
+    int cur = int(k_s - base); // where the still open row's part inside this stream begins
+    T carry = T(0);            // lane 0: that part's sum over the chunks already done
+    int k = cur;
+    int kb = 0;
+    do {
+      const int kend = kb + kWsChunk < k_e ? kb + kWsChunk : k_e;
+      // ---- products of this chunk: two quads per lane -----------------------------
+      T p[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kk = kb + 4 * (lane + 32 * u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          p[u][j] = T(0);
+        if (kk < kend && kk + 4 > k) {
+          Quad<I> c;
+          Quad<T> v;
+          if (kk + 4 <= arr_end) {
+            c = ld_stream_quad(ci + kk);
+            if (!has_perm) {
+              v = ld_stream_quad(va + kk);
+            } else {
+              const Quad<O> pi = ld_stream_quad(perm + base + kk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                v.v[j] = ld_ro(values + pi.v[j]);
+            }
+          } else { // the arrays' last partial quad
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool in = kk + j < arr_end;
+              c.v[j] = in ? ld_stream(ci + kk + j) : I(0);
+              v.v[j] = !in ? T(0)
+                           : (has_perm ? ld_ro(values + perm[base + kk + j])
+                                       : ld_stream(va + kk + j));
+            }
+          }
+          T xv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            xv[j] = ld_ro(x + c.v[j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            p[u][j] = (kk + j >= k && kk + j < kend) ? v.v[j] * xv[j] : T(0);
+        }
+      }
+      // ---- rows that end inside the chunk -------------------------------------------
+      int re = 0x7fffffff;
+      if (lane < rows_left)
+        re = int(int64_t(rowptr[row + 1 + lane]) - base);
+      unsigned mask = __ballot_sync(0xffffffffu, re <= kend);
+      if (mask == 0u) {
+        // the chunk lies inside one row: no shared memory, straight to the shuffle tree
+        T sum = ((p[0][0] + p[0][1]) + (p[0][2] + p[0][3])) +
+                ((p[1][0] + p[1][1]) + (p[1][2] + p[1][3]));
+        sum = warp_reduce_sum(sum);
+        carry += sum;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          Vec4<T> q;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            q.v[j] = p[u][j];
+          *reinterpret_cast<Vec4<T>*>(slab + 4 * (lane + 32 * u)) = q;
+        }
+        __syncwarp();
+        for (;;) {
+          const int nready = __popc(mask); // a prefix of the lanes: row ends ascend
+          int b = __shfl_up_sync(0xffffffffu, re, 1);
+          if (lane == 0)
+            b = cur > kb ? cur : kb; // what lies before this chunk is in `carry`
+          const bool mine = lane < nready;
+          const int len = mine ? re - b : 0;
+          if (mine && len <= 32) {
+            const T* q = slab + (b - kb);
+            T sum = T(0);
+#pragma unroll 1
+            for (int i = 0; i < len; ++i) // storage order, like the reference
+              sum += q[i];
+            if (lane == 0)
+              sum += carry;
+            put(row + lane, alpha * sum);
+          }
+          unsigned todo = __ballot_sync(0xffffffffu, mine && len > 32);
+          while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int bb = __shfl_sync(0xffffffffu, b, src) - kb;
+            const int ee = __shfl_sync(0xffffffffu, re, src) - kb;
+            T sum = T(0);
+            for (int i = bb + lane; i < ee; i += 32)
+              sum += slab[i];
+            sum = warp_reduce_sum(sum);
+            if (lane == 0) {
+              if (src == 0)
+                sum += carry;
+              put(row + src, alpha * sum);
+            }
+          }
+          cur = __shfl_sync(0xffffffffu, re, nready - 1);
+          row += nready;
+          rows_left -= nready;
+          carry = T(0);
+          if (nready < 32 || rows_left <= 0)
+            break;
+          re = 0x7fffffff;
+          if (lane < rows_left)
+            re = int(int64_t(rowptr[row + 1 + lane]) - base);
+          mask = __ballot_sync(0xffffffffu, re <= kend);
+          if (mask == 0u)
+            break;
+        }
+        // what follows the last row end belongs to the row still open
+        if (cur < kend) {
+          T sum = T(0);
+          for (int i = cur - kb + lane; i < kend - kb; i += 32)
+            sum += slab[i];
+          carry = warp_reduce_sum(sum);
+        }
+        __syncwarp(); // the slab is rewritten by the next chunk
+      }
+      k = kend;
+      kb += kWsChunk;
+    } while (k < k_e);
+    if (lane == 0) {
+      if (row_e < rows && cur < k_e) {
+        carry_row[s] = row_e;
+        carry_val[s] = carry;
+      } else {
+        carry_row[s] = -1;
+      }
+    }
+  }
+}
+
+// ============================================================================
 // Fallback kernel: one tile per CTA
 // ============================================================================
 template <typename T, typename I, typename O>
@@ -939,37 +1149,20 @@ spmv_carry_fixup_kernel(const int64_t* __restrict__ carry_row,
   }
 }
 
-// Tiles [T0, T1) of the partition (the whole product: [0, num_tiles)).  A proper
-// sub-range is one chunk of a host-buffer execute (host_exec.cu): chunks are launched
-// in ascending order on one stream, and each completes the rows that end in its tiles.
+// Units [T0, T1) of the active partition — tiles for the tile kernels, warp streams
+// for the warp-stream kernel (the whole product: all of them).  A proper sub-range is
+// one chunk of a host-buffer execute (host_exec.cu): chunks are launched in ascending
+// order on one stream, and each completes the rows that end in its units.
 template <typename T, typename I, typename O>
-int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
+int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void* values,
                 const void* x, void* y, int64_t T0, int64_t T1) {
   if (p->num_tiles == 0 && p->barrier.n == 0)
     return SPBLAS_B200_SUCCESS; // (a rank with no rows still takes part in the barrier)
   const int64_t ntiles = T1 - T0;
   const T a = *static_cast<const T*>(alpha);
-  const auto aligned16 = [](const void* q) {
-    return (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
-  };
   const bool perm = p->csr_perm != nullptr;
-  const int vec_ok = aligned16(p->csr_colind) && (perm || aligned16(values)) &&
-                     (!perm || aligned16(p->csr_perm));
-  if (p->num_tiles > int64_t(0x7fffffff))
-    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "too many tiles for one launch");
+  const int vec_ok = spmv_vec_ok(p, values);
   const int64_t nnz_end = p->base + p->nnz;
-
-  // Kernel choice.  The pipelined kernel wins when most tiles are uniform (stencils,
-  // fixed-degree graphs: coalesced row-ordered gathers, no row-end lookups); matrices
-  // with mixed row lengths are bound by random gathers of x, where the one-tile-per-CTA
-  // kernel's higher occupancy (64 warps/SM of gathers in flight) is worth more.
-  int variant = p->forced_variant >= 0
-                    ? p->forced_variant
-                    : (2 * p->uniform_tiles >= p->num_tiles ? kVariantPipelined
-                                                            : kVariantMergeTile);
-  if (!vec_ok)
-    variant = kVariantMergeTile; // bulk copies need 16-byte aligned arrays
-  p->spmv_variant = variant;
 
   ScatterArgs<T> sc;
   sc.n = p->scatter.n;
@@ -997,7 +1190,26 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
     bar.epoch = ++p->barrier_epoch;
 
   cudaError_t e = cudaSuccess;
-  if (ntiles <= 0) {
+  // the carry arrays and the unit count of the active partition
+  const bool ws = variant == kVariantWarpStream;
+  const int64_t units = ws ? p->ws_streams : p->num_tiles;
+  const int64_t* d_carry_row =
+      static_cast<const int64_t*>(ws ? p->ws_carry_row.p : p->carry_row.p);
+  const T* d_carry_val = static_cast<const T*>(ws ? p->ws_carry_val.p : p->carry_val.p);
+  if (ntiles > 0 && ws) {
+    int64_t grid = (ntiles + kWsWarps - 1) / kWsWarps;
+    if (grid > int64_t(p->num_sms) * ws_ctas_per_sm<T, I>())
+      grid = int64_t(p->num_sms) * ws_ctas_per_sm<T, I>();
+    spmv_warp_stream_kernel<T, I, O><<<unsigned(grid), kWsWarps * 32, 0, p->stream>>>(
+        static_cast<const O*>(p->csr_rowptr), static_cast<const I*>(p->csr_colind),
+        static_cast<const T*>(values), static_cast<const O*>(p->csr_perm),
+        static_cast<const T*>(x), static_cast<T*>(y), a,
+        static_cast<const int64_t*>(p->ws_starts.p), T0, ntiles, p->csr_rows, nnz_end,
+        static_cast<int64_t*>(p->ws_carry_row.p), static_cast<T*>(p->ws_carry_val.p), sc);
+    e = cudaGetLastError();
+    if (e != cudaSuccess)
+      return cuda_fail(p, e, "spmv_warp_stream_kernel");
+  } else if (ntiles <= 0) {
     // nothing to multiply: only the fix-up kernel's barrier runs
   } else if (variant == kVariantPipelined) {
     // Pipeline shape: stages x (header + tile data) of shared memory per CTA; shared
@@ -1060,14 +1272,12 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
   // carries whose row ends inside [T0, T1): runs whose last tile is in [T0 - 1, T1 - 1)
   // (the partition's last tile never carries, so the final chunk simply runs to T1)
   const int64_t fix_lo = T0 > 0 ? T0 - 1 : 0;
-  const int64_t fix_hi = T1 >= p->num_tiles ? p->num_tiles : T1 - 1;
+  const int64_t fix_hi = T1 >= units ? units : T1 - 1;
   const int64_t fix_n = fix_hi > fix_lo ? fix_hi - fix_lo : 0;
   const unsigned fgrid = fix_n > 0 ? unsigned((fix_n + 255) / 256) : 1u;
   if (fix_n > 0 || bar.n > 0) {
     spmv_carry_fixup_kernel<T><<<fgrid, 256, 0, p->stream>>>(
-        static_cast<const int64_t*>(p->carry_row.p),
-        static_cast<const T*>(p->carry_val.p), fix_lo, fix_hi, p->num_tiles,
-        static_cast<T*>(y), a, sc, bar);
+        d_carry_row, d_carry_val, fix_lo, fix_hi, units, static_cast<T*>(y), a, sc, bar);
     e = cudaGetLastError();
     if (e != cudaSuccess)
       return cuda_fail(p, e, "spmv_carry_fixup_kernel");
@@ -1079,31 +1289,72 @@ int launch_spmv(spblas_b200_plan* p, const void* alpha, const void* values,
 }
 
 template <typename T>
-int dispatch_index(spblas_b200_plan* p, const void* alpha, const void* values,
+int dispatch_index(spblas_b200_plan* p, int variant, const void* alpha, const void* values,
                    const void* x, void* y, int64_t T0, int64_t T1) {
   const bool i64 = p->idx_type == SPBLAS_B200_I64;
   const bool o64 = p->off_type == SPBLAS_B200_I64;
   if (!i64 && !o64)
-    return launch_spmv<T, int32_t, int32_t>(p, alpha, values, x, y, T0, T1);
+    return launch_spmv<T, int32_t, int32_t>(p, variant, alpha, values, x, y, T0, T1);
   if (!i64 && o64)
-    return launch_spmv<T, int32_t, int64_t>(p, alpha, values, x, y, T0, T1);
+    return launch_spmv<T, int32_t, int64_t>(p, variant, alpha, values, x, y, T0, T1);
   if (i64 && !o64)
-    return launch_spmv<T, int64_t, int32_t>(p, alpha, values, x, y, T0, T1);
-  return launch_spmv<T, int64_t, int64_t>(p, alpha, values, x, y, T0, T1);
+    return launch_spmv<T, int64_t, int32_t>(p, variant, alpha, values, x, y, T0, T1);
+  return launch_spmv<T, int64_t, int64_t>(p, variant, alpha, values, x, y, T0, T1);
 }
 
 } // namespace
 
+// Which kernel runs this product, and the partition it runs on.  The pipelined kernel
+// wins when most tiles are uniform (stencils, fixed-degree graphs: coalesced row-ordered
+// gathers, no row-end lookups); matrices with mixed row lengths are bound by random
+// gathers of x, where autonomous warps keep the L1 tag stage busiest (warp streams).
+// Arrays that are not 16-byte aligned fall back to the one-tile-per-CTA kernel.
+int prepare_spmv(spblas_b200_plan* p, int val_type, const void* values, int* variant,
+                 const int64_t** starts, int64_t* units) {
+  int v = p->forced_variant >= 0
+              ? p->forced_variant
+              : (2 * p->uniform_tiles >= p->num_tiles ? kVariantPipelined : kVariantWarpStream);
+  if (!spmv_vec_ok(p, values))
+    v = kVariantMergeTile;
+  if (v != kVariantMergeTile && v != kVariantPipelined && v != kVariantWarpStream)
+    v = kVariantMergeTile;
+  if (p->num_tiles > int64_t(0x7fffffff))
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "too many tiles for one launch");
+  if (v == kVariantWarpStream && p->ws_streams < 0) {
+    const bool wide = type_size_val(val_type) == 8 || p->idx_type == SPBLAS_B200_I64;
+    const int64_t resident =
+        int64_t(p->num_sms) * (wide ? kWsCtasPerSm - 1 : kWsCtasPerSm) * kWsWarps;
+    if (int rc = build_ws_partition(p, resident))
+      return rc;
+  }
+  p->spmv_variant = v;
+  *variant = v;
+  if (starts)
+    *starts = static_cast<const int64_t*>(v == kVariantWarpStream ? p->ws_starts.p
+                                                                  : p->tile_starts.p);
+  if (units)
+    *units = v == kVariantWarpStream ? p->ws_streams : p->num_tiles;
+  return SPBLAS_B200_SUCCESS;
+}
+
 int run_spmv_tiles(spblas_b200_plan* p, int val_type, const void* alpha,
                    const void* values, const void* x, void* y, int64_t T0,
                    int64_t T1) {
+  int variant = 0;
+  int64_t units = 0;
+  if (int rc = prepare_spmv(p, val_type, values, &variant, nullptr, &units))
+    return rc;
+  if (T1 < 0) { // the whole product
+    T0 = 0;
+    T1 = units;
+  }
   switch (val_type) {
   case SPBLAS_B200_F32:
-    return dispatch_index<float>(p, alpha, values, x, y, T0, T1);
+    return dispatch_index<float>(p, variant, alpha, values, x, y, T0, T1);
   case SPBLAS_B200_F64:
-    return dispatch_index<double>(p, alpha, values, x, y, T0, T1);
+    return dispatch_index<double>(p, variant, alpha, values, x, y, T0, T1);
   case SPBLAS_B200_S32:
-    return dispatch_index<int32_t>(p, alpha, values, x, y, T0, T1);
+    return dispatch_index<int32_t>(p, variant, alpha, values, x, y, T0, T1);
   default:
     return fail(p, SPBLAS_B200_NOT_SUPPORTED, "unknown value type");
   }
@@ -1112,7 +1363,7 @@ int run_spmv_tiles(spblas_b200_plan* p, int val_type, const void* alpha,
 int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
              const void* values, const void* x, void* y) {
   p->last_launches = 0;
-  return run_spmv_tiles(p, val_type, alpha, values, x, y, 0, p->num_tiles);
+  return run_spmv_tiles(p, val_type, alpha, values, x, y, 0, -1);
 }
 
 } // namespace b200

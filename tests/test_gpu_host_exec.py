@@ -36,7 +36,7 @@ def _host_vs_device(a, x, m, vt, alpha=None):
 
 
 @pytest.mark.parametrize("chunks", ["1", "3", "16", "64"])
-@pytest.mark.parametrize("variant", ["0", "1"])
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
 @pytest.mark.parametrize("kind", ["short", "mixed", "hub", "empty"])
 def test_host_execute_bit_identical(cuda, oracle, monkeypatch, kind, variant, chunks):
     monkeypatch.setenv("SPBLAS_B200_HOST_CHUNKS", chunks)

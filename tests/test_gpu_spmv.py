@@ -292,3 +292,53 @@ def test_csc_spmv(cuda, oracle):
         # same addition order as the reference's column scatter -> compare tightly
         sb.multiply(info, sb.scaled(5, a), xd, yd)
         assert oracle.expect_eq_tolerance(g["csc_spmv_ascaled_5"], yd.cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("ws_items", ["256", "0"])
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("kind", ["short", "mixed", "hub", "long", "empty"])
+def test_spmv_every_kernel_variant(cuda, oracle, monkeypatch, kind, variant, ws_items):
+    """Each SpMV kernel (0 one tile per CTA, 1 TMA pipeline, 2 warp streams) forced on every
+    row-length mix, in fp32 / fp64 / int32 (exact), on a CSR matrix, on a row-block shard
+    with a non-zero base and on a CSC matrix (value permutation).  ws_items = 256 makes a
+    warp walk many short streams (carries between streams, rows spanning several)."""
+    if variant != 2 and ws_items == "0":
+        pytest.skip("stream length only matters to the warp-stream kernel")
+    monkeypatch.setenv("SPBLAS_B200_SPMV_VARIANT", str(variant))
+    if ws_items != "0":
+        monkeypatch.setenv("SPBLAS_B200_WS_ITEMS", ws_items)
+    for vt in (np.float32, np.float64, np.int32):
+        rng = np.random.default_rng(zlib.crc32(f"var{kind}{vt.__name__}".encode()))
+        m, n = 5003, 2777
+        v, rp, ci, x = _random_csr(rng, m, n, kind, vt, np.int32, np.int32)
+        alpha = 3 if vt == np.int32 else 0.75
+        y_ref = oracle.spmv("csr", (m, n), rp, ci, v, x, alpha_a=alpha)
+        bound = None if vt == np.int32 else oracle.abs_rowsum(rp, ci, v, x, alpha)
+        a = csr_on_device(v, rp, ci, (m, n))
+        xd = dev(x)
+        info = sb.multiply_inspect(a, xd, torch.empty(m, dtype=xd.dtype, device="cuda"))
+        y = gpu_spmv(a, x, m, vt, info=info, alpha_a=alpha)
+        assert info.spmv_variant == variant
+        assert_rows_within_bound(y, y_ref, rp, bound, f"variant {variant} {kind} {vt.__name__}")
+        info.close()
+        # a row block of the same matrix: rowptr keeps the global base
+        r0, r1 = 777, 4100
+        blk = sb.csr_view(a.values, a.rowptr[r0:r1 + 1], a.colind, (r1 - r0, n),
+                          int(rp[r1] - rp[r0]))
+        info = sb.multiply_inspect(blk, xd, torch.empty(r1 - r0, dtype=xd.dtype, device="cuda"))
+        yb = gpu_spmv(blk, x, r1 - r0, vt, info=info, alpha_a=alpha)
+        assert_rows_within_bound(yb, y_ref[r0:r1], rp[r0:r1 + 1],
+                                 None if bound is None else bound[r0:r1], f"shard variant {variant}")
+        info.close()
+    # CSC: the kernels gather the values through the permutation built by the inspect
+    rng = np.random.default_rng(zlib.crc32(f"varcsc{kind}".encode()))
+    m, n = 2203, 3001
+    v, cp, ri, _ = _random_csr(rng, n, m, kind, np.float64, np.int32, np.int32)
+    x = rng.standard_normal(n)
+    ac = csc_on_device(v, cp, ri, (m, n))
+    info = sb.multiply_inspect(ac, dev(x), torch.empty(m, dtype=torch.float64, device="cuda"))
+    yc = gpu_spmv(ac, x, m, np.float64, info=info)
+    t_rp, t_ci, perm = oracle.csc_row_major_image((m, n), cp, ri)
+    assert_rows_within_bound(yc, oracle.spmv("csc", (m, n), cp, ri, v, x), t_rp,
+                             oracle.abs_rowsum(t_rp, t_ci, v[perm], x), f"csc variant {variant}")
+    info.close()
