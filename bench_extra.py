@@ -54,6 +54,30 @@ def _bytes_spmm(nnz, m, n, k, sT, sI=4, sO=4):
     return nnz * (sT + sI) + (m + 1) * sO + n * k * sT + m * k * sT
 
 
+def gather_ceiling(sb_cabi, operands, steps, with_values=True):
+    """ms of the gather probe (csrc/probe.cu) on the workload's own colind / values / x: the
+    same loads as SpMV and nothing else.  `operands`: list of (colind, values, x) rotated
+    like the timed loop.  Best over the probe's occupancy settings."""
+    import ctypes as C
+    L = sb_cabi.lib()
+    ci0, v0, x0 = operands[0]
+    vt = sb_cabi.F32 if v0.dtype == torch.float32 else sb_cabi.F64
+    it = sb_cabi.I32 if ci0.dtype == torch.int32 else sb_cabi.I64
+    out = torch.empty(148 * 8 * 256 * 2, dtype=v0.dtype, device=v0.device)
+    stream = torch.cuda.current_stream().cuda_stream
+    best = None
+    for ctas in (4, 6, 8):
+        def fn(i):
+            ci, v, x = operands[i % len(operands)]
+            st = L.spblas_b200_probe_gather(stream, it, vt, ci.numel(), ci.data_ptr(),
+                                            v.data_ptr() if with_values else None,
+                                            x.data_ptr(), out.data_ptr(), ctas)
+            assert st == 0, st
+        ms = _time_loop(fn, steps, 3)
+        best = ms if best is None else min(best, ms)
+    return best
+
+
 def _time_loop(fn, steps, warmup):
     for i in range(warmup):
         fn(i)
@@ -93,6 +117,7 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         cmp_args = ("spmv", [(m, n, t[0].rowptr, t[0].colind, t[0].values, t[1],
                               torch.empty_like(t[2])) for t in mats], 1.2)
         result_of = lambda: mats[0][2]
+        probe_ops = [(t[0].colind, t[0].values, t[1]) for t in mats]
     elif wl == "c4":
         v, rp, ci, shape = G.rmat_csr(24, 16, seed=24, dtype=torch.float32, device=dev)
         m, n = shape
@@ -115,6 +140,7 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         launches_of = lambda: info.total_launches
         cmp_args = ("spmv", [(m, n, rp, ci, v, x, torch.empty_like(y))], 1.0)
         result_of = lambda: y
+        probe_ops = [(ci, v, x)]
     else:
         k = 32 if wl == "c3k32" else 128
         m = n = 2_000_000
@@ -157,6 +183,17 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         cusparse["max_abs_result"] = ref
         best = min(vv for kk, vv in cusparse.items() if kk.startswith("CUSPARSE_"))
         cusparse["ours_over_best_cusparse"] = best / ms
+    gather = None
+    if not wl.startswith("c3"):
+        from spblas_reference_b200 import _cabi
+        pms = gather_ceiling(_cabi, probe_ops, K)
+        gather = {"probe_ms": pms, "frac_of_probe": pms / ms,
+                  "gathers_per_ns": nnz / (pms * 1e6),
+                  "what": "csrc/probe.cu on this workload's colind/values/x: 128-bit streaming "
+                          "loads + one gather of x per nonzero, no rows, no reduction — the "
+                          "ceiling any SpMV kernel has on this index stream (the L1 tag stage "
+                          "takes one 128-byte line per cycle per SM: 148 x 1.965 GHz = 291 "
+                          "gathers/ns)"}
     line = {
         "metric": "CSR SpMM GFLOP/s" if wl.startswith("c3") else "CSR SpMV GFLOP/s",
         "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": 1, "steps": K,
@@ -169,7 +206,8 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
                      "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
                      # what the launch really moved through DRAM (ncu), per second: for the
                      # gather-bound configs THIS is what sits against the HBM peak
-                     "dram_gbs_at_ncu_traffic": (traffic / (ms * 1e-3) / 1e9) if traffic else None},
+                     "dram_gbs_at_ncu_traffic": (traffic / (ms * 1e-3) / 1e9) if traffic else None,
+                     "gather_ceiling": gather},
         "clocks": clocks, "gpu_launches": int(launches),
         "cusparse": cusparse,
     }
@@ -240,6 +278,14 @@ def run_c5(args, sb, G, dev, peak, peak_src, sampler, world, rank, barrier, max_
     total_nnz = int(sum_over_ranks(nnz_loc))
     nbytes = nnz_loc * 12 + (m_loc + 1) * 8 + n * 8 + m_loc * 8   # full replicated x
     achieved = nbytes / (kern_ms * 1e-3) / 1e9
+    from spblas_reference_b200 import _cabi
+    xp = G.dense_uniform((n,), 5, torch.float64, dev)
+    pms = gather_ceiling(_cabi, [(ci, v, xp)], max(5, K // 2))
+    del xp
+    gather = {"probe_ms": pms, "frac_of_probe": pms / kern_ms,
+              "gathers_per_ns": nnz_loc / (pms * 1e6),
+              "what": "csrc/probe.cu on rank 0's colind/values and a full x: the same loads as "
+                      "SpMV and nothing else — the ceiling of this index stream"}
     if rank == 0:
         line = {
             "metric": "CSR SpMV GFLOP/s", "value": 2.0 * total_nnz / (step_ms * 1e-3) / 1e9,
@@ -260,6 +306,7 @@ def run_c5(args, sb, G, dev, peak, peak_src, sampler, world, rank, barrier, max_
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
+                         "gather_ceiling": gather,
                          "note": "random 8-byte gathers of x (1 GB at scale 27) cost a 32-byte "
                                  "sector each: the compulsory-bytes roofline is not reachable "
                                  "(SURVEY 8d caveat)"},

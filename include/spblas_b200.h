@@ -240,6 +240,18 @@ SPBLAS_B200_API const char* spblas_b200_last_error_once(void);
 SPBLAS_B200_API const char* spblas_b200_status_string(int status);
 SPBLAS_B200_API int spblas_b200_version(void);
 
+/* Measurement aid (csrc/probe.cu), not part of the multiply path: streams d_colind[nnz]
+   (and d_values[nnz] unless NULL) with 128-bit loads and gathers d_x through it, one
+   accumulator per thread written to d_out[148 * ctas_per_sm * 256 at most 303104
+   elements].  bench.py times it to report the gather ceiling of a workload's own
+   index stream next to the compulsory-bytes roofline.  Arrays must be 16-byte aligned;
+   the tail nnz % 4 is ignored. */
+SPBLAS_B200_API int spblas_b200_probe_gather(void* cuda_stream, int idx_type,
+                                             int val_type, int64_t nnz,
+                                             const void* d_colind, const void* d_values,
+                                             const void* d_x, void* d_out,
+                                             int ctas_per_sm);
+
 /* Debug/tuning knob (also read from the environment variable
    SPBLAS_B200_SPMV_VARIANT at plan creation): force a SpMV kernel variant for
    ncu A/B runs.  -1 = automatic. */

@@ -36,7 +36,7 @@ SYMBOLS = (
     "spblas_b200_last_error", "spblas_b200_last_error_once", "spblas_b200_status_string",
     "spblas_b200_version", "spblas_b200_plan_force_variant",
     "spblas_b200_plan_set_scatter", "spblas_b200_plan_set_barrier",
-    "spblas_b200_spmv_host",
+    "spblas_b200_spmv_host", "spblas_b200_probe_gather",
 )
 
 
@@ -84,6 +84,8 @@ def lib() -> C.CDLL:
     L.spblas_b200_spmv.restype = i32
     L.spblas_b200_spmv_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.spblas_b200_spmv_host.restype = i32
+    L.spblas_b200_probe_gather.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, i32]
+    L.spblas_b200_probe_gather.restype = i32
     L.spblas_b200_spmm.argtypes = [vp, i32, vp, vp, vp, i64, vp, i64, i64]
     L.spblas_b200_spmm.restype = i32
     L.spblas_b200_spmv_once.argtypes = [vp, i32, i64, i64, i64, vp, vp, i32, i32, i32, vp,

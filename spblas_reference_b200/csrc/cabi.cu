@@ -143,6 +143,10 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
   int l2 = 0;
   if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, p->device) == cudaSuccess && l2 > 0)
     p->l2_bytes = l2;
+  int smem_sm = 0;
+  if (cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, p->device) ==
+          cudaSuccess && smem_sm > 0)
+    p->smem_per_sm = size_t(smem_sm);
   if (const char* v = std::getenv("SPBLAS_B200_SPMV_VARIANT"))
     p->forced_variant = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_TILE_ITEMS")) {
@@ -158,6 +162,8 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->consumer_warps = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_WS_ITEMS"))
     p->ws_items_override = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_WS_CARVEOUT"))
+    p->ws_carveout = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_HOST_CHUNKS"))
     p->host_chunks_override = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_SPMM_VARIANT"))

@@ -76,6 +76,7 @@ struct spblas_b200_plan {
   int device = 0;
   int num_sms = 148;
   int64_t l2_bytes = 126ll << 20;
+  size_t smem_per_sm = 228u << 10;
 
   // ---- structure as given by the caller (not owned) -------------------------
   bool inspected = false;
@@ -133,6 +134,7 @@ struct spblas_b200_plan {
   int64_t ws_streams = -1;         // -1: table not built for the current structure
   int ws_items = 0;                // merge items per stream
   int ws_items_override = 0;       // env SPBLAS_B200_WS_ITEMS (tuning)
+  int ws_carveout = -1;            // shared-memory carve-out in percent (env SPBLAS_B200_WS_CARVEOUT; -1 default)
   b200::DeviceBuffer ws_starts;    // int64 (row, nnz) pairs, ws_streams + 1 entries
   b200::DeviceBuffer ws_carry_row; // int64 per stream
   b200::DeviceBuffer ws_carry_val; // 8 bytes per stream

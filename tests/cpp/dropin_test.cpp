@@ -170,6 +170,21 @@ void spmv_cases() {
     spblas::multiply(moved, a, x_span, y_span);
     expect_all_close(host_spmv<T, I, O>(m, rowptr, colind, values, x, T(1)), d_y.to_host());
 
+    g_case = "SpMV host vectors (pipelined upload / kernels / download)";
+    {
+      std::vector<T> y_host(m, T(77));
+      device_array<T> x_stage(std::size_t(n), T(0)), y_stage(std::size_t(m), T(0));
+      std::span<T> xs(x_stage.get(), n), ys(y_stage.get(), m);
+      std::span<T> xh(x.data(), n), yh(y_host.data(), m);
+      spblas::multiply_execute_host(moved, spblas::scaled(2.0f, a), xh, yh, xs, ys);
+      CUDA_OK(cudaDeviceSynchronize());
+      spblas::multiply(moved, spblas::scaled(2.0f, a), x_span, y_span);
+      ++g_checks;
+      if (y_host != d_y.to_host())
+        fail("host-vector execute differs from the device-vector execute");
+      expect_all_close(host_spmv<T, I, O>(m, rowptr, colind, values, x, T(2)), y_host);
+    }
+
     g_case = "SpMV matrix_opt";
     spblas::matrix_opt a_opt(a);
     auto info2 = spblas::multiply_inspect(a_opt, x_span, y_span);
