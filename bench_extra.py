@@ -54,6 +54,37 @@ def _bytes_spmm(nnz, m, n, k, sT, sI=4, sO=4):
     return nnz * (sT + sI) + (m + 1) * sO + n * k * sT + m * k * sT
 
 
+def cpu_baseline(kind, m, n, rp, ci, v, xin, alpha, rows_sample, flops_per_nnz, what):
+    """The reference's own CPU multiply (oracle/_ref when built from /root/reference, else the
+    oracle port) on a bounded sample — the first `rows_sample` rows of the same matrix against
+    the same dense operand — on the box's host cores (1 thread: the reference is serial)."""
+    import numpy as np
+    from oracle import oracle as O
+    O.build()
+    R = int(min(m, rows_sample))
+    rph = rp[:R + 1].cpu().numpy()
+    nnz_r = int(rph[-1] - rph[0])
+    cih, vh = ci[:nnz_r + int(rph[0])].cpu().numpy(), v[:nnz_r + int(rph[0])].cpu().numpy()
+    xh = xin.cpu().numpy()
+    impl, kindname = ("reference", "reference") if O.have_ref() else ("oracle", "port")
+    fn = O.spmv if kind == "spmv" else O.spmm
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        try:
+            fn("csr", (R, n), rph, cih, vh, xh, alpha_a=alpha, impl=impl)
+        except AttributeError:              # type combination the reference shim does not export
+            impl, kindname = "oracle", "port"
+            fn("csr", (R, n), rph, cih, vh, xh, alpha_a=alpha, impl=impl)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": flops_per_nnz * nnz_r / best / 1e9, "unit": "GFLOP/s", "cores": 1,
+            "kind": kindname, "seconds": best,
+            "sample": f"{what}: rows [0, {R}) of {m} ({nnz_r} stored entries), best of 2; the "
+                      "reference CPU multiply is serial (1 thread)",
+            "host_cores_available": os.cpu_count()}
+
+
 def gather_ceiling(sb_cabi, operands, steps, with_values=True):
     """ms of the gather probe (csrc/probe.cu) on the workload's own colind / values / x: the
     same loads as SpMV and nothing else.  `operands`: list of (colind, values, x) rotated
@@ -118,6 +149,8 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
                               torch.empty_like(t[2])) for t in mats], 1.2)
         result_of = lambda: mats[0][2]
         probe_ops = [(t[0].colind, t[0].values, t[1]) for t in mats]
+        cpu_args = ("spmv", m, n, mats[0][0].rowptr, mats[0][0].colind, mats[0][0].values,
+                    mats[0][1], 1.2, m, 2.0, "C1 full product")
     elif wl == "c4":
         v, rp, ci, shape = G.rmat_csr(24, 16, seed=24, dtype=torch.float32, device=dev)
         m, n = shape
@@ -141,6 +174,7 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         cmp_args = ("spmv", [(m, n, rp, ci, v, x, torch.empty_like(y))], 1.0)
         result_of = lambda: y
         probe_ops = [(ci, v, x)]
+        cpu_args = ("spmv", m, n, rp, ci, v, x, None, m, 2.0, "C4 full product")
     else:
         k = 32 if wl == "c3k32" else 128
         m = n = 2_000_000
@@ -160,6 +194,8 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         launches_of = lambda: info.total_launches
         cmp_args = ("spmm", [(m, n, rp, ci, v, B, torch.empty_like(C))], 1.0)
         result_of = lambda: C
+        cpu_args = ("spmm", m, n, rp, ci, v, B, None, 400_000 if k == 32 else 100_000, 2.0 * k,
+                    f"C3 k={k} row block")
 
     sampler.start()
     l0 = launches_of()
@@ -210,6 +246,7 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
                      "gather_ceiling": gather},
         "clocks": clocks, "gpu_launches": int(launches),
         "cusparse": cusparse,
+        "cpu_baseline": None if args.no_cpu_baseline else cpu_baseline(*cpu_args),
     }
     print(json.dumps(line), flush=True)
 
@@ -248,7 +285,7 @@ def run_c5(args, sb, G, dev, peak, peak_src, sampler, world, rank, barrier, max_
     op = ShardedSpMV(n, blocks, (0, n), lambda x, y: sb.multiply_execute(info, a_scaled, x, y),
                      torch.float64, dev, info=info,
                      fused=None if os.environ.get("SPBLAS_B200_FUSED", "1") != "0" else False,
-                     multicast=os.environ.get("SPBLAS_B200_MULTICAST", "0") == "1")
+                     multicast={"1": True, "0": False}.get(os.environ.get("SPBLAS_B200_MULTICAST")))
     op.set_x(x0)
     del x0, y0
     for _ in range(W):

@@ -194,6 +194,27 @@ SPBLAS_B200_API int spblas_b200_spmm_once(
     int val_type, const void* alpha, const void* d_values, const void* d_B,
     int64_t ldb, void* d_C, int64_t ldc, int64_t k);
 
+/* ---- transpose(a, b): B = A^T, both CSR ---------------------------------------
+
+   Replaces transpose_inspect / transpose (algorithms/transpose.hpp:8-13,
+   algorithms/transpose_impl.hpp:9-60: count, exclusive scan, scatter, serial).  The
+   inspect phase sorts the structure once (stable: within a row of B the entries keep A's
+   storage order, exactly the reference's scatter order, so B is bit-identical to the
+   reference's); the execute phase copies the structure into B's arrays and moves the
+   values through the permutation, so re-transposing after a change of values costs one
+   gather pass.  The same plan also multiplies: it IS the plan of transposed(a), usable
+   with spblas_b200_spmv / _spmm for y = A^T x.
+     transpose_inspect: A is m x n with d_rowptr[m+1], d_colind[nnz].
+     transpose:         d_t_rowptr[n+1] (zero-based), d_t_colind[nnz], d_t_values[nnz]. */
+SPBLAS_B200_API int spblas_b200_transpose_inspect(spblas_b200_plan* plan, int64_t m,
+                                                  int64_t n, int64_t nnz,
+                                                  const void* d_rowptr,
+                                                  const void* d_colind, int off_type,
+                                                  int idx_type);
+SPBLAS_B200_API int spblas_b200_transpose(spblas_b200_plan* plan, int val_type,
+                                          const void* d_values, void* d_t_rowptr,
+                                          void* d_t_colind, void* d_t_values);
+
 /* ---- fused exchange for row-block sharded iterations (y -> x) ----------------
 
    The reference has no multi-GPU path; this is the B200 side of SURVEY.md 8(e).

@@ -208,6 +208,29 @@ def csc_row_major_image(shape, colptr, rowind):
     return t_rowptr, t_colind[:nnz], perm[:nnz]
 
 
+def transpose(shape, rowptr, colind, values, impl="oracle"):
+    """B = A^T as CSR following reference algorithms/transpose_impl.hpp:14-53.
+    Returns (b_values, b_rowptr, b_colind) with the dtypes of the inputs."""
+    m, n = shape
+    rowptr, colind, values = _c(rowptr), _c(colind), _c(values)
+    tn, inn, on = _names(values, colind, rowptr)
+    nnz = int(rowptr[-1] - rowptr[0]) if len(rowptr) else 0
+    b_rowptr = np.full(n + 1, -1, dtype=rowptr.dtype)
+    b_colind = np.full(max(nnz, 1), -1, dtype=colind.dtype)
+    b_values = np.zeros(max(nnz, 1), dtype=values.dtype)
+    if impl == "oracle":
+        fn = getattr(lib(), f"oracle_csr_transpose_{tn}_{inn}_{on}")
+        fn.restype = None
+        fn(C.c_int64(m), C.c_int64(n), _p(rowptr), _p(colind), _p(values), _p(b_rowptr),
+           _p(b_colind), _p(b_values))
+    else:
+        fn = getattr(ref(), f"ref_csr_transpose_{tn}_{inn}_{on}")
+        fn.restype = None
+        fn(C.c_int64(m), C.c_int64(n), C.c_int64(nnz), _p(rowptr), _p(colind), _p(values),
+           _p(b_rowptr), _p(b_colind), _p(b_values))
+    return b_values[:nnz], b_rowptr, b_colind[:nnz]
+
+
 # ------------------------------------------------------------------ reference fixtures
 def ref_generate_csr(m, n, nnz, seed=0, dtype=np.float32):
     """spblas::generate_csr<T, int32, int32> (reference backend/generate.hpp:106-120)."""

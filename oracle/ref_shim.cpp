@@ -10,6 +10,9 @@
 // spblas::index_t = size_t and an operation_info_t without backend state
 // (detail/types.hpp:28-31, detail/operation_info_t.hpp:28-104), which must never meet
 // the B200 backend's definitions of the same names in one symbol namespace.
+#include <numeric>
+#include <stdexcept>
+
 #include <spblas/spblas.hpp>
 
 #include <cstdint>
@@ -119,6 +122,25 @@ void spmm(A a, int has_aa, T alpha_a, int has_ab, T alpha_b, const T* B,
         make_csc<T, I, O>(m, n, nnz, colptr, rowind, values), has_aa, alpha_a,     \
         has_ab, alpha_b, B, n, k, C, m, inspect);                                  \
   }
+
+// transpose_inspect + transpose(info, a, b) exactly as test/gtest/transpose_test.cpp:33-34
+#define DEF_TRANSPOSE(T, TN, I, IN, O, ON)                                         \
+  REF_API void ref_csr_transpose_##TN##_##IN##_##ON(                               \
+      int64_t m, int64_t n, int64_t nnz, const O* rowptr, const I* colind,         \
+      const T* values, O* b_rowptr, I* b_colind, T* b_values) {                    \
+    auto a = make_csr<T, I, O>(m, n, nnz, rowptr, colind, values);                 \
+    spblas::csr_view<T, I, O> b(b_values, b_rowptr, b_colind,                      \
+                                spblas::index<I>(I(n), I(m)), O(nnz));             \
+    auto info = spblas::transpose_inspect(a, b);                                   \
+    spblas::transpose(info, a, b);                                                 \
+  }
+
+DEF_TRANSPOSE(float, f32, int32_t, i32, int32_t, i32)
+DEF_TRANSPOSE(float, f32, int32_t, i32, int64_t, i64)
+DEF_TRANSPOSE(double, f64, int32_t, i32, int32_t, i32)
+DEF_TRANSPOSE(double, f64, int32_t, i32, int64_t, i64)
+DEF_TRANSPOSE(int32_t, s32, int32_t, i32, int32_t, i32)
+DEF_TRANSPOSE(float, f32, int64_t, i64, int64_t, i64)
 
 DEF_OPS(float, f32, int32_t, i32, int32_t, i32)
 DEF_OPS(float, f32, int32_t, i32, int64_t, i64)

@@ -10,12 +10,13 @@ no compute and no CPU fallback.
 from . import _cabi
 from .multiply import (multiply, multiply_execute, multiply_execute_host, multiply_inspect,
                        operation_info_t)
+from .transpose import transpose, transpose_inspect
 from .views import (conjugated, csc_view, csr_view, matrix_opt, scaled, scaled_view,
                     transposed)
 
 __all__ = [
     "multiply", "multiply_inspect", "multiply_execute", "multiply_execute_host",
-    "operation_info_t",
+    "operation_info_t", "transpose", "transpose_inspect",
     "csr_view", "csc_view", "scaled", "scaled_view", "transposed", "matrix_opt",
     "conjugated",
 ]

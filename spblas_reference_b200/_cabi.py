@@ -37,6 +37,7 @@ SYMBOLS = (
     "spblas_b200_version", "spblas_b200_plan_force_variant",
     "spblas_b200_plan_set_scatter", "spblas_b200_plan_set_barrier",
     "spblas_b200_spmv_host", "spblas_b200_probe_gather",
+    "spblas_b200_transpose_inspect", "spblas_b200_transpose",
 )
 
 
@@ -84,6 +85,10 @@ def lib() -> C.CDLL:
     L.spblas_b200_spmv.restype = i32
     L.spblas_b200_spmv_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.spblas_b200_spmv_host.restype = i32
+    L.spblas_b200_transpose_inspect.argtypes = [vp, i64, i64, i64, vp, vp, i32, i32]
+    L.spblas_b200_transpose_inspect.restype = i32
+    L.spblas_b200_transpose.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.spblas_b200_transpose.restype = i32
     L.spblas_b200_probe_gather.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, i32]
     L.spblas_b200_probe_gather.restype = i32
     L.spblas_b200_spmm.argtypes = [vp, i32, vp, vp, vp, i64, vp, i64, i64]

@@ -309,6 +309,29 @@ int spblas_b200_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
   return run_spmv(p, val_type, alpha, d_values, d_x, d_y);
 }
 
+int spblas_b200_transpose_inspect(spblas_b200_plan* p, int64_t m, int64_t n, int64_t nnz,
+                                  const void* d_rowptr, const void* d_colind,
+                                  int off_type, int idx_type) {
+  // A (m x n, CSR) read column-major IS A^T (n x m) stored as CSC over the same arrays:
+  // the CSC inspect builds the row-major image of A^T, i.e. its CSR structure
+  return spblas_b200_inspect(p, SPBLAS_B200_CSC, n, m, nnz, d_rowptr, d_colind, off_type,
+                             idx_type, 1, SPBLAS_B200_INSPECT_LIGHT);
+}
+
+int spblas_b200_transpose(spblas_b200_plan* p, int val_type, const void* d_values,
+                          void* d_t_rowptr, void* d_t_colind, void* d_t_values) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  if (!p->inspected || p->format != SPBLAS_B200_CSC)
+    return fail(p, SPBLAS_B200_NOT_INSPECTED, "transpose called before transpose_inspect");
+  if (!valid_value_type(val_type))
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "value type must be f32, f64 or s32");
+  if (!d_t_rowptr || (p->nnz > 0 && (!d_values || !d_t_colind || !d_t_values)))
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null device pointer");
+  return run_transpose(p, val_type, d_values, d_t_rowptr, d_t_colind, d_t_values);
+}
+
 int spblas_b200_spmv_host(spblas_b200_plan* p, int val_type, const void* alpha,
                           const void* d_values, const void* h_x, void* h_y,
                           void* d_x, void* d_y) {

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "device_utils.cuh"
 #include "plan.hpp"
 
 namespace b200 {
@@ -594,6 +595,53 @@ int build_ws_partition(spblas_b200_plan* p, int64_t resident_warps) {
 int build_stream_partition(spblas_b200_plan* p, int64_t streams) {
   return p->off_type == SPBLAS_B200_I64 ? stream_partition_typed<int64_t>(p, streams)
                                         : stream_partition_typed<int32_t>(p, streams);
+}
+
+namespace {
+
+// b_values[q] = a_values[perm[q]]: the value half of transpose(a, b).  perm is streamed,
+// the values are gathered (each is read exactly once), the output is streamed.
+template <typename W, typename O>
+__global__ void __launch_bounds__(256)
+gather_values_kernel(const W* __restrict__ values, const O* __restrict__ perm, int64_t nnz,
+                     W* __restrict__ out) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nnz; q += stride)
+    out[q] = ld_ro(values + int64_t(ld_stream(perm + q)));
+}
+
+template <typename O>
+int transpose_typed(spblas_b200_plan* p, size_t val_bytes, const void* values, void* t_values) {
+  const int64_t nnz = p->nnz;
+  if (nnz == 0)
+    return SPBLAS_B200_SUCCESS;
+  const int grid = int(std::min<int64_t>((nnz + 255) / 256, int64_t(p->num_sms) * 16));
+  const O* perm = static_cast<const O*>(p->csr_perm);
+  if (val_bytes == 8)
+    gather_values_kernel<uint64_t, O><<<grid, 256, 0, p->stream>>>(
+        static_cast<const uint64_t*>(values), perm, nnz, static_cast<uint64_t*>(t_values));
+  else
+    gather_values_kernel<uint32_t, O><<<grid, 256, 0, p->stream>>>(
+        static_cast<const uint32_t*>(values), perm, nnz, static_cast<uint32_t*>(t_values));
+  return launch_ok(p, "gather_values_kernel");
+}
+
+} // namespace
+
+// transpose(info, a, b) after transpose_inspect: the plan holds the CSR structure of
+// A^T (it was inspected as the CSC matrix A^T over A's own arrays); the structure is
+// copied out and the values follow through the permutation.
+int run_transpose(spblas_b200_plan* p, int val_type, const void* values, void* t_rowptr,
+                  void* t_colind, void* t_values) {
+  const size_t so = type_size_idx(p->off_type), si = type_size_idx(p->idx_type);
+  B200_CUDA_TRY(p, cudaMemcpyAsync(t_rowptr, p->csr_rowptr, size_t(p->csr_rows + 1) * so,
+                                   cudaMemcpyDeviceToDevice, p->stream));
+  if (p->nnz > 0)
+    B200_CUDA_TRY(p, cudaMemcpyAsync(t_colind, p->csr_colind, size_t(p->nnz) * si,
+                                     cudaMemcpyDeviceToDevice, p->stream));
+  return p->off_type == SPBLAS_B200_I64
+             ? transpose_typed<int64_t>(p, type_size_val(val_type), values, t_values)
+             : transpose_typed<int32_t>(p, type_size_val(val_type), values, t_values);
 }
 
 int inspect_structure(spblas_b200_plan* p, int flags) {

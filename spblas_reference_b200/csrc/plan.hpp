@@ -194,6 +194,8 @@ void release(DeviceBuffer& b);
 int inspect_structure(spblas_b200_plan* p, int flags);
 int build_stream_partition(spblas_b200_plan* p, int64_t streams);
 int build_ws_partition(spblas_b200_plan* p, int64_t resident_warps);
+int run_transpose(spblas_b200_plan* p, int val_type, const void* values, void* t_rowptr,
+                  void* t_colind, void* t_values);
 // spmv.cu
 int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
              const void* values, const void* x, void* y);

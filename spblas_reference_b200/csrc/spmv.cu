@@ -169,6 +169,22 @@ __device__ __forceinline__ void multimem_store(T* p, T v) {
   }
 }
 
+// does any destination want a row of [r_begin, r_end)?  Quick reject on the union of the
+// ranges, then the ranges themselves: two peers that want the first and the last grid
+// line of a block (halo of a banded matrix) have a union that spans the whole block, and
+// only the tiles at its two ends may pay for the per-row checks.
+template <typename T>
+__device__ __forceinline__ bool wants_rows(const ScatterArgs<T>& sc, int64_t r_begin,
+                                           int64_t r_end) {
+  if (sc.n == 0 || r_begin >= sc.hi_max || r_end <= sc.lo_min)
+    return false;
+#pragma unroll 1
+  for (int d = 0; d < sc.n; ++d)
+    if (r_begin < sc.hi[d] && r_end > sc.lo[d])
+      return true;
+  return false;
+}
+
 template <typename T>
 __device__ __forceinline__ void scatter_store(const ScatterArgs<T>& sc, int64_t row, T v) {
 #pragma unroll 1
@@ -554,7 +570,7 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
     const O* rowend = reinterpret_cast<const O*>(data + hp->off_rowend);
 
     // does a peer need rows of this tile?
-    const bool scat = sc.n > 0 && row0 < sc.hi_max && row0 + nr > sc.lo_min;
+    const bool scat = wants_rows(sc, row0, row0 + nr);
     auto put = [&](int64_t row, T v) {
       y[row] = v;
       if (scat)
@@ -740,7 +756,7 @@ spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ coli
     int64_t row = starts[2 * s];
     const int64_t k_s = starts[2 * s + 1];
     const int64_t row_e = starts[2 * s + 2];
-    const bool scat = sc.n > 0 && row < sc.hi_max && row_e > sc.lo_min;
+    const bool scat = wants_rows(sc, row, row_e);
     auto put = [&](int64_t r, T v) {
       y[r] = v;
       if (scat)
@@ -943,7 +959,7 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
 
   if (tid == 0)
     s_nlong = 0;
-  const bool scat = sc.n > 0 && row0 < sc.hi_max && row1 > sc.lo_min;
+  const bool scat = wants_rows(sc, row0, row1);
   auto put = [&](int64_t row, T v) {
     y[row] = v;
     if (scat)

@@ -302,6 +302,85 @@ void csc_spmm_case() {
   expect_all_close(ref, d_c.to_host());
 }
 
+// ---- transpose(a, b): the body of test/gtest/transpose_test.cpp on device memory --------------
+template <typename T, typename I, typename O>
+void transpose_cases() {
+  for (auto [m, n, nnz] : dims) {
+    auto [values, rowptr, colind, shape, nnz_] = spblas::generate_csr<T, I, O>(m, n, nnz);
+    device_array<T> d_values(values);
+    device_array<O> d_rowptr(rowptr);
+    device_array<I> d_colind(colind);
+    spblas::csr_view<T, I, O> a(d_values.get(), d_rowptr.get(), d_colind.get(), shape, O(nnz));
+    device_array<T> d_bv(std::size_t(nnz), T(0));
+    device_array<O> d_brp(std::size_t(n) + 1, O(-1));
+    device_array<I> d_bci(std::size_t(nnz), I(-1));
+    spblas::csr_view<T, I, O> b(d_bv.get(), d_brp.get(), d_bci.get(),
+                                spblas::index<I>(I(n), I(m)), O(nnz));
+    g_case = "transpose";
+    auto info = spblas::transpose_inspect(a, b);
+    spblas::transpose(info, a, b);
+    // the reference's host algorithm (algorithms/transpose_impl.hpp:33-50), restated
+    std::vector<O> rp(n + 1, 0);
+    std::vector<I> ci(nnz);
+    std::vector<T> v(nnz);
+    for (int i = 0; i < m; ++i)
+      for (O p = rowptr[i]; p < rowptr[i + 1]; ++p)
+        rp[colind[p] + 1]++;
+    O run = 0;
+    for (int j = 0; j <= n; ++j) {
+      const O c = rp[j];
+      rp[j] = run;
+      run += c;
+    }
+    for (int i = 0; i < m; ++i)
+      for (O p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+        const O out = rp[colind[p] + 1]++;
+        ci[out] = I(i);
+        v[out] = values[p];
+      }
+    ++g_checks;
+    if (d_brp.to_host() != rp || d_bci.to_host() != ci || d_bv.to_host() != v)
+      fail("transpose differs from the reference algorithm");
+    ++g_checks;
+    if (std::size_t(b.size()) != std::size_t(nnz))
+      fail("b.update() did not set the stored-entry count");
+    // the overload without info, and B used as an operand afterwards: B x = A^T x
+    spblas::transpose(a, b);
+    std::vector<T> x(m, T(1));
+    device_array<T> d_x(x), d_y(std::size_t(n), T(0)), d_y2(std::size_t(n), T(0));
+    spblas::multiply(b, std::span<T>(d_x.get(), m), std::span<T>(d_y.get(), n));
+    spblas::multiply(spblas::transposed(a), std::span<T>(d_x.get(), m),
+                     std::span<T>(d_y2.get(), n));
+    expect_all_close(d_y.to_host(), d_y2.to_host());
+  }
+  g_case = "transpose errors";
+  auto [values, rowptr, colind, shape, nnz] = spblas::generate_csr<T, I, O>(40, 30, 100);
+  device_array<T> d_values(values), d_bv(std::size_t(99), T(0));
+  device_array<O> d_rowptr(rowptr), d_brp(std::size_t(31), O(0));
+  device_array<I> d_colind(colind), d_bci(std::size_t(99), I(0));
+  spblas::csr_view<T, I, O> a(d_values.get(), d_rowptr.get(), d_colind.get(), shape, O(100));
+  ++g_checks;
+  try {
+    spblas::csr_view<T, I, O> bad(d_bv.get(), d_brp.get(), d_bci.get(),
+                                  spblas::index<I>(I(31), I(40)), O(99));
+    spblas::transpose(a, bad);
+    fail("no exception for incompatible dimensions");
+  } catch (const std::invalid_argument& e) {
+    if (std::string(e.what()) != "transpose: matrix dimensions are incompatible.")
+      fail(std::string("unexpected message: ") + e.what());
+  }
+  ++g_checks;
+  try {
+    spblas::csr_view<T, I, O> small(d_bv.get(), d_brp.get(), d_bci.get(),
+                                    spblas::index<I>(I(30), I(40)), O(99));
+    spblas::transpose(a, small);
+    fail("no exception for an output that is too small");
+  } catch (const std::runtime_error& e) {
+    if (std::string(e.what()) != "transpose: Transpose ran out of memory.")
+      fail(std::string("unexpected message: ") + e.what());
+  }
+}
+
 // ---- error behaviour --------------------------------------------------------------------------
 void error_cases() {
   using T = float;
@@ -349,6 +428,8 @@ int main() {
   spmm_cases<float>();
   spmm_cases<double>();
   csc_spmm_case();
+  transpose_cases<float, spblas::index_t, spblas::offset_t>();
+  transpose_cases<double, std::int32_t, std::int64_t>();
   error_cases();
   std::printf("dropin_test: %d checks, %d failures\n", g_checks, g_failures);
   return g_failures == 0 ? 0 : 1;

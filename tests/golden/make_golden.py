@@ -49,6 +49,10 @@ def main():
                 else:
                     out[f"dense_B_{k}"] = B
                     out[f"{fmt}_spmm_{k}"] = Cm
+        # transpose(a, b) on the CSR fixture (test/gtest/transpose_test.cpp:15-34)
+        tv, trp, tci = O.transpose((m, n), out["csr_ptr"], out["csr_ind"], out["csr_values"],
+                                   impl="reference")
+        out["csr_transpose_values"], out["csr_transpose_ptr"], out["csr_transpose_ind"] = tv, trp, tci
         path = os.path.join(HERE, f"dims_{m}_{n}_{nnz}.npz")
         np.savez_compressed(path, **out)
         print(path, os.path.getsize(path) // 1024, "KiB")

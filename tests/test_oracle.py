@@ -218,3 +218,64 @@ def test_csc_row_major_image(oracle):
     for i in range(100):
         seg = perm[t_rp[i]:t_rp[i + 1]]
         assert (np.diff(seg) > 0).all()                 # stable: storage order kept
+
+
+# ---------------------------------------------------------------------------------------
+# transpose(a, b): oracle restatement of algorithms/transpose_impl.hpp:14-53
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dims", DIMS)
+def test_transpose_matches_golden_and_reference_test(oracle, dims):
+    """Bit-exact against the committed output of the real spblas::transpose, and the
+    reference test's own check (test/gtest/transpose_test.cpp:36-87: the COO triples of B,
+    rows and columns swapped, are a permutation of A's)."""
+    g = golden(*dims)
+    m, n, _ = dims
+    v, rp, ci = g["csr_values"], g["csr_ptr"], g["csr_ind"]
+    tv, trp, tci = oracle.transpose((m, n), rp, ci, v)
+    assert np.array_equal(tv, g["csr_transpose_values"])
+    assert np.array_equal(trp, g["csr_transpose_ptr"])
+    assert np.array_equal(tci, g["csr_transpose_ind"])
+    a_rows = np.repeat(np.arange(m), np.diff(rp))
+    b_rows = np.repeat(np.arange(n), np.diff(trp))
+    a_coo = sorted(zip(ci.tolist(), a_rows.tolist(), v.tolist()))
+    b_coo = sorted(zip(b_rows.tolist(), tci.tolist(), tv.tolist()))
+    assert a_coo == b_coo
+    assert trp[0] == 0 and trp[-1] == len(ci)
+
+
+def test_transpose_against_real_reference_when_present(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(12)
+    for (vt, it, ot) in [(np.float32, np.int32, np.int32), (np.float32, np.int32, np.int64),
+                         (np.float64, np.int32, np.int32), (np.float64, np.int32, np.int64),
+                         (np.int32, np.int32, np.int32), (np.float32, np.int64, np.int64)]:
+        m, n = 311, 97
+        lens = rng.integers(0, 30, size=m)
+        lens[3] = 0
+        lens[200] = 250                                  # duplicates inside a row are certain
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(ot)
+        ci = rng.integers(0, n, size=int(rp[-1])).astype(it)          # unsorted
+        v = (rng.integers(-99, 99, size=len(ci)) if vt == np.int32
+             else rng.standard_normal(len(ci))).astype(vt)
+        got = oracle.transpose((m, n), rp, ci, v)
+        want = oracle.transpose((m, n), rp, ci, v, impl="reference")
+        for a, b in zip(got, want):
+            assert a.dtype == b.dtype and np.array_equal(a, b)
+    # empty matrix, and a matrix with no entries in some columns
+    e = oracle.transpose((4, 3), np.zeros(5, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32))
+    assert e[1].tolist() == [0, 0, 0, 0]
+
+
+def test_transpose_equals_csc_image(oracle):
+    """transpose(A) is the row-major image of A^T given as CSC over A's arrays — the identity
+    the GPU implementation rests on (csrc/inspect.cu: run_transpose)."""
+    rng = np.random.default_rng(13)
+    m, n = 150, 220
+    lens = rng.integers(0, 9, size=m)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ci = rng.integers(0, n, size=int(rp[-1])).astype(np.int32)
+    v = rng.standard_normal(len(ci)).astype(np.float32)
+    tv, trp, tci = oracle.transpose((m, n), rp, ci, v)
+    i_rp, i_ci, perm = oracle.csc_row_major_image((n, m), rp, ci)
+    assert np.array_equal(trp, i_rp) and np.array_equal(tci, i_ci) and np.array_equal(tv, v[perm])
