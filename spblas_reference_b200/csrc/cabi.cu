@@ -160,8 +160,11 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->ctas_per_sm = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_CONSUMER_WARPS"))
     p->consumer_warps = std::atoi(v);
-  if (const char* v = std::getenv("SPBLAS_B200_WS_ITEMS"))
-    p->ws_items_override = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_WS_ITEMS")) {
+    const int t = std::atoi(v);
+    if (t >= 256 && t <= (1 << 20))
+      p->ws_items_override = t;
+  }
   if (const char* v = std::getenv("SPBLAS_B200_WS_CARVEOUT"))
     p->ws_carveout = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_HOST_CHUNKS"))

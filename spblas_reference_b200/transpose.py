@@ -59,11 +59,18 @@ def _inspect(info: operation_info_t, a, b):
     info.result_nnz = a.nnz
 
 
-def transpose_inspect(a, b) -> operation_info_t:
-    """Analyse A's structure for B = A^T (a no-op in the CPU reference, transpose_impl.hpp:9-12;
-    here: stable sort of the column indices carrying the storage position)."""
+def transpose_inspect(*args):
+    """transpose_inspect(a, b) -> operation_info_t, or transpose_inspect(info, a, b) to
+    re-inspect into an existing info (its device buffers are reused).  Analyses A's
+    structure for B = A^T (a no-op in the CPU reference, transpose_impl.hpp:9-12; here:
+    stable sort of the column indices carrying the storage position)."""
+    if len(args) == 3 and isinstance(args[0], operation_info_t):
+        _inspect(*args)
+        return None
+    if len(args) != 2:
+        raise TypeError("transpose_inspect(a, b) or transpose_inspect(info, a, b)")
     info = operation_info_t()
-    _inspect(info, a, b)
+    _inspect(info, *args)
     return info
 
 
