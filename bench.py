@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2",
-                    choices=["c1", "c2", "c3k32", "c3k128", "c4", "c5", "t1", "t4"])
+                    choices=["c1", "c2", "c3k32", "c3k128", "c4", "c5", "t1", "t4", "c1t", "c4t"])
     ap.add_argument("--scale", type=int, default=0,
                     help="C5 R-MAT scale (default 24 + log2(N): 16.7M rows per GPU)")
     ap.add_argument("--grid", type=int, default=4096, help="C2 grid edge (per GPU)")

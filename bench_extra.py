@@ -12,7 +12,7 @@ import time
 import torch
 
 
-def cusparse_compare(kind, operands, steps, scale=1.0):
+def cusparse_compare(kind, operands, steps, scale=1.0, transpose=False):
     """ms per product of NVIDIA cuSPARSE — what the reference's NVIDIA backend calls
     (vendor/cusparse/spmv_impl.hpp:80-84, CUSPARSE_SPMV_ALG_DEFAULT) — on the same operands,
     same box, same timing loop (scripts/cusparse_comparator.py; comparator only).  `operands`
@@ -30,7 +30,8 @@ def cusparse_compare(kind, operands, steps, scale=1.0):
             runs = []
             for (m, n, rp, ci, v, xin, yout) in operands:
                 if kind == "spmv":
-                    runs.append(cs.spmv(m, n, rp, ci, v, xin, yout, alpha=scale, alg=alg))
+                    runs.append(cs.spmv(m, n, rp, ci, v, xin, yout, alpha=scale, alg=alg,
+                                        transpose=transpose))
                 else:
                     runs.append(cs.spmm(m, n, xin.shape[1], rp, ci, v, xin, yout, alpha=scale, alg=alg))
             state = {"i": 0}
@@ -151,6 +152,42 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         probe_ops = [(t[0].colind, t[0].values, t[1]) for t in mats]
         cpu_args = ("spmv", m, n, mats[0][0].rowptr, mats[0][0].colind, mats[0][0].values,
                     mats[0][1], 1.2, m, 2.0, "C1 full product")
+    elif wl in ("c1t", "c4t"):
+        # y = A^T x through transposed(a) (the second half of the alternating
+        # A x / A^T y loop of notes/spmv.hpp:14-22): the inspect phase builds the row-major
+        # image of A^T once, the execute kernels gather the values through its permutation
+        if wl == "c1t":
+            v, rp, ci, shape = G.uniform_random_csr(1_000_000, 1_000_000, 10, seed=0,
+                                                    dtype=torch.float32, device=dev)
+            name = "C1 matrix, y = A^T x via transposed(a), fp32/int32"
+        else:
+            v, rp, ci, shape = G.rmat_csr(22, 16, seed=24, dtype=torch.float32, device=dev)
+            name = "R-MAT scale 22 (edge factor 16), y = A^T x via transposed(a), fp32/int32"
+        m, n = shape
+        nnz = int(ci.numel())
+        a = sb.transposed(sb.csr_view(v, rp, ci, shape, nnz))          # n x m
+        if os.environ.get("SPBLAS_B200_MATRIX_OPT", "1") != "0":
+            # matrix_opt: the plan may keep the values gathered in image order (the solver
+            # loop's values are static); =0 measures the gather-through-permutation path
+            a = sb.matrix_opt(a)
+            name += ", matrix_opt (values cached at inspect)"
+        x = G.dense_uniform((m,), 5, torch.float32, dev)
+        y = torch.empty(n, device=dev)
+        t0 = time.perf_counter()
+        info = sb.multiply_inspect(a, x, y)
+        torch.cuda.synchronize()
+        extra["inspect_ms"] = (time.perf_counter() - t0) * 1e3
+
+        def fn(i):
+            sb.multiply_execute(info, a, x, y)
+        flops, nbytes, dtype = 2.0 * nnz, _bytes_spmv(nnz, n, m, 4), "f32"
+        extra["l2_policy"] = "inputs larger than L2"
+        launches_of = lambda: info.total_launches
+        cmp_args = ("spmv", [(m, n, rp, ci, v, x, torch.empty_like(y))], 1.0)
+        cmp_transpose = True
+        result_of = lambda: y
+        probe_ops = None
+        cpu_args = None
     elif wl == "c4":
         v, rp, ci, shape = G.rmat_csr(24, 16, seed=24, dtype=torch.float32, device=dev)
         m, n = shape
@@ -214,7 +251,8 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
     if wl.startswith("c3"):
         extra["spmm_variant"] = info.spmm_variant
     # same-box vendor comparator (the reference's NVIDIA backend is a cuSPARSE wrapper)
-    cusparse = cusparse_compare(cmp_args[0], cmp_args[1], K, cmp_args[2])
+    cusparse = cusparse_compare(cmp_args[0], cmp_args[1], K, cmp_args[2],
+                                transpose=locals().get("cmp_transpose", False))
     if cusparse and "unavailable" not in cusparse:
         ours, theirs = result_of(), cmp_args[1][0][6]
         fn(0)                                          # operand set 0 again
@@ -226,7 +264,7 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         best = min(vv for kk, vv in cusparse.items() if kk.startswith("CUSPARSE_"))
         cusparse["ours_over_best_cusparse"] = best / ms
     gather = None
-    if not wl.startswith("c3"):
+    if not wl.startswith("c3") and probe_ops is not None:
         from spblas_reference_b200 import _cabi
         pms = gather_ceiling(_cabi, probe_ops, K)
         gather = {"probe_ms": pms, "frac_of_probe": pms / ms,
@@ -252,7 +290,7 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
                      "gather_ceiling": gather},
         "clocks": clocks, "gpu_launches": int(launches),
         "cusparse": cusparse,
-        "cpu_baseline": None if args.no_cpu_baseline else cpu_baseline(*cpu_args),
+        "cpu_baseline": None if (args.no_cpu_baseline or cpu_args is None) else cpu_baseline(*cpu_args),
     }
     print(json.dumps(line), flush=True)
 

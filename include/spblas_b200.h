@@ -146,6 +146,20 @@ SPBLAS_B200_API int spblas_b200_inspect(spblas_b200_plan* plan, int format,
                                         int off_type, int idx_type,
                                         int64_t k_hint, int flags);
 
+/* Optional, for CSC operands (and transposed(csr), which is one): gather the values
+   once into the order of the inspected row-major image, so that later executes stream
+   them like a CSR matrix's instead of fetching each through the permutation (a
+   scattered 4/8-byte read per entry: 4.6x slower on an R-MAT).  The C++ headers call it
+   from multiply_inspect when the operand is wrapped in matrix_opt — the reference's
+   marker for "the backend may keep optimised state for this matrix"
+   (views/matrix_opt_impl.hpp:14-93; vendor/onemkl_sycl/spmv_impl.hpp:46-53 calls
+   optimize_gemv under the same condition).  Contract, as with oneMKL's optimize: the
+   values must not change until the next inspect / cache_values.  The cache is used
+   only by executes that pass the same d_values pointer and value type; d_values = NULL
+   drops it; a no-op for CSR plans. */
+SPBLAS_B200_API int spblas_b200_plan_cache_values(spblas_b200_plan* plan, int val_type,
+                                                  const void* d_values);
+
 /* ---- execute ------------------------------------------------------------ */
 
 /* y[m] = alpha * A * x[n]   (beta = 0: y is overwritten, stale contents —

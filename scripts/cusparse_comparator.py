@@ -54,18 +54,20 @@ class CuSparse:
             _VAL[values.dtype]), "cusparseCreateCsr")
         return d
 
-    def spmv(self, m, n, rowptr, colind, values, x, y, alpha=1.0, alg=0):
-        """Returns a zero-argument callable that enqueues y = alpha A x."""
+    def spmv(self, m, n, rowptr, colind, values, x, y, alpha=1.0, alg=0, transpose=False):
+        """Returns a zero-argument callable that enqueues y = alpha A x (or alpha A^T x:
+        CUSPARSE_OPERATION_TRANSPOSE, what get_transpose.hpp:19-29 selects for a CSC base)."""
+        op = 1 if transpose else 0
         T = C.c_float if values.dtype == torch.float32 else C.c_double
         a, b = T(alpha), T(0)
         A = self._csr(m, n, rowptr, colind, values)
         X, Y = C.c_void_p(), C.c_void_p()
-        self._chk(self.L.cusparseCreateDnVec(C.byref(X), C.c_int64(n), C.c_void_p(x.data_ptr()),
+        self._chk(self.L.cusparseCreateDnVec(C.byref(X), C.c_int64(x.numel()), C.c_void_p(x.data_ptr()),
                                              _VAL[x.dtype]), "cusparseCreateDnVec")
-        self._chk(self.L.cusparseCreateDnVec(C.byref(Y), C.c_int64(m), C.c_void_p(y.data_ptr()),
+        self._chk(self.L.cusparseCreateDnVec(C.byref(Y), C.c_int64(y.numel()), C.c_void_p(y.data_ptr()),
                                              _VAL[y.dtype]), "cusparseCreateDnVec")
         size = C.c_size_t(0)
-        self._chk(self.L.cusparseSpMV_bufferSize(self.h, 0, C.byref(a), A, X, C.byref(b), Y,
+        self._chk(self.L.cusparseSpMV_bufferSize(self.h, op, C.byref(a), A, X, C.byref(b), Y,
                                                  _VAL[values.dtype], alg, C.byref(size)),
                   "cusparseSpMV_bufferSize")
         buf = torch.empty(max(size.value, 16), dtype=torch.uint8, device=values.device)
@@ -74,7 +76,7 @@ class CuSparse:
         bp = C.c_void_p(buf.data_ptr())
 
         def run():
-            st = L.cusparseSpMV(h, 0, C.byref(a), A, X, C.byref(b), Y, ct, alg, bp)
+            st = L.cusparseSpMV(h, op, C.byref(a), A, X, C.byref(b), Y, ct, alg, bp)
             if st != 0:
                 raise RuntimeError(f"cusparseSpMV failed with cusparseStatus {st}")
         return run

@@ -38,6 +38,7 @@ SYMBOLS = (
     "spblas_b200_plan_set_scatter", "spblas_b200_plan_set_barrier",
     "spblas_b200_spmv_host", "spblas_b200_probe_gather",
     "spblas_b200_transpose_inspect", "spblas_b200_transpose",
+    "spblas_b200_plan_cache_values",
 )
 
 
@@ -85,6 +86,8 @@ def lib() -> C.CDLL:
     L.spblas_b200_spmv.restype = i32
     L.spblas_b200_spmv_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.spblas_b200_spmv_host.restype = i32
+    L.spblas_b200_plan_cache_values.argtypes = [vp, i32, vp]
+    L.spblas_b200_plan_cache_values.restype = i32
     L.spblas_b200_transpose_inspect.argtypes = [vp, i64, i64, i64, vp, vp, i32, i32]
     L.spblas_b200_transpose_inspect.restype = i32
     L.spblas_b200_transpose.argtypes = [vp, i32, vp, vp, vp, vp]

@@ -65,7 +65,7 @@ void release_all(spblas_b200_plan* p) {
                           &p->carry_val,   &p->segments,   &p->seg_partial,
                           &p->seg_counter, &p->stats,      &p->spmm_starts,
                           &p->spmm_carry_row, &p->spmm_carry_val, &p->barrier_state,
-                          &p->ws_starts, &p->ws_carry_row, &p->ws_carry_val};
+                          &p->ws_starts, &p->ws_carry_row, &p->ws_carry_val, &p->own_values};
   for (DeviceBuffer* b : bufs)
     release(*b);
   release(p->hc_colmax);
@@ -76,6 +76,25 @@ bool valid_index_type(int t) { return t == SPBLAS_B200_I32 || t == SPBLAS_B200_I
 bool valid_value_type(int t) {
   return t == SPBLAS_B200_F32 || t == SPBLAS_B200_F64 || t == SPBLAS_B200_S32;
 }
+
+// While alive, executes run on the plan's cached (image-order) values instead of gathering
+// the caller's through the permutation — if the caller passed the pointer and type the
+// cache was built from.
+struct CachedValues {
+  spblas_b200_plan* p;
+  const void* saved_perm;
+  bool active;
+  CachedValues(spblas_b200_plan* plan, int val_type, const void*& values) : p(plan) {
+    active = p->cached_values && p->csr_perm != nullptr && values == p->cached_src &&
+             val_type == p->cached_val_type;
+    saved_perm = p->csr_perm;
+    if (active) {
+      p->csr_perm = nullptr;
+      values = p->own_values.p;
+    }
+  }
+  ~CachedValues() { p->csr_perm = saved_perm; }
+};
 
 thread_local std::string g_once_error;
 struct OncePlanHolder {
@@ -260,6 +279,7 @@ int spblas_b200_inspect(spblas_b200_plan* p, int format, int64_t m, int64_t n,
   p->err.clear();
   p->inspected = false;
   p->host_chunks = 0; // the chunk table belongs to the previous structure
+  p->cached_values = false;
   if (format != SPBLAS_B200_CSR && format != SPBLAS_B200_CSC)
     return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "format must be CSR or CSC");
   if (!valid_index_type(off_type) || !valid_index_type(idx_type))
@@ -309,7 +329,31 @@ int spblas_b200_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
   if ((p->nnz > 0 && !d_values) || (p->n > 0 && p->nnz > 0 && !d_x) ||
       (p->m > 0 && !d_y))
     return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null device pointer");
+  CachedValues scope(p, val_type, d_values);
   return run_spmv(p, val_type, alpha, d_values, d_x, d_y);
+}
+
+int spblas_b200_plan_cache_values(spblas_b200_plan* p, int val_type, const void* d_values) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  p->cached_values = false;
+  if (!d_values)
+    return SPBLAS_B200_SUCCESS; // cache dropped
+  if (!p->inspected)
+    return fail(p, SPBLAS_B200_NOT_INSPECTED, "cache_values called before inspect");
+  if (!valid_value_type(val_type))
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "value type must be f32, f64 or s32");
+  if (p->csr_perm == nullptr || p->nnz == 0)
+    return SPBLAS_B200_SUCCESS; // CSR operands are streamed in place: nothing to cache
+  if (int rc = reserve(p, p->own_values, size_t(p->nnz) * type_size_val(val_type)))
+    return rc;
+  if (int rc = gather_permuted_values(p, val_type, d_values, p->own_values.p))
+    return rc;
+  p->cached_values = true;
+  p->cached_val_type = val_type;
+  p->cached_src = d_values;
+  return SPBLAS_B200_SUCCESS;
 }
 
 int spblas_b200_transpose_inspect(spblas_b200_plan* p, int64_t m, int64_t n, int64_t nnz,
@@ -350,6 +394,7 @@ int spblas_b200_spmv_host(spblas_b200_plan* p, int val_type, const void* alpha,
   if ((p->nnz > 0 && !d_values) || (p->n > 0 && p->nnz > 0 && (!h_x || !d_x)) ||
       (p->m > 0 && (!h_y || !d_y)))
     return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null pointer");
+  CachedValues scope(p, val_type, d_values);
   return run_spmv_host(p, val_type, alpha, d_values, h_x, h_y, d_x, d_y);
 }
 
@@ -371,6 +416,7 @@ int spblas_b200_spmm(spblas_b200_plan* p, int val_type, const void* alpha,
     return fail(p, SPBLAS_B200_SHAPE_MISMATCH, "leading dimension smaller than k");
   if (k > 0 && ((p->nnz > 0 && (!d_values || !d_B)) || (p->m > 0 && !d_C)))
     return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null device pointer");
+  CachedValues scope(p, val_type, d_values);
   return run_spmm(p, val_type, alpha, d_values, d_B, ldb, d_C, ldc, k);
 }
 

@@ -644,6 +644,13 @@ int run_transpose(spblas_b200_plan* p, int val_type, const void* values, void* t
              : transpose_typed<int32_t>(p, type_size_val(val_type), values, t_values);
 }
 
+// out[q] = values[perm[q]] for the whole image (the value half of run_transpose)
+int gather_permuted_values(spblas_b200_plan* p, int val_type, const void* values, void* out) {
+  return p->off_type == SPBLAS_B200_I64
+             ? transpose_typed<int64_t>(p, type_size_val(val_type), values, out)
+             : transpose_typed<int32_t>(p, type_size_val(val_type), values, out);
+}
+
 int inspect_structure(spblas_b200_plan* p, int flags) {
   const bool i64 = p->idx_type == SPBLAS_B200_I64;
   const bool o64 = p->off_type == SPBLAS_B200_I64;

@@ -99,6 +99,15 @@ struct spblas_b200_plan {
   b200::DeviceBuffer own_rowptr, own_colind, own_perm, sort_tmp0, sort_tmp1,
       sort_tmp2, sort_ws;
 
+  // ---- cached values of a CSC / transposed operand (spblas_b200_plan_cache_values) ---
+  // values[perm[q]] gathered once into image order, so that executes stream them like a
+  // CSR matrix's instead of gathering through the permutation.  Valid only for calls
+  // that pass the same values pointer and type; dropped by the next inspect.
+  bool cached_values = false;
+  int cached_val_type = 0;
+  const void* cached_src = nullptr;
+  b200::DeviceBuffer own_values;
+
   // ---- merge-path partition --------------------------------------------------
   int tile_items = b200::kSpmvTileItems;
   int tile_items_override = 0; // env SPBLAS_B200_TILE_ITEMS (tuning)
@@ -196,6 +205,7 @@ int build_stream_partition(spblas_b200_plan* p, int64_t streams);
 int build_ws_partition(spblas_b200_plan* p, int64_t resident_warps);
 int run_transpose(spblas_b200_plan* p, int val_type, const void* values, void* t_rowptr,
                   void* t_colind, void* t_values);
+int gather_permuted_values(spblas_b200_plan* p, int val_type, const void* values, void* out);
 // spmv.cu
 int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
              const void* values, const void* x, void* y);

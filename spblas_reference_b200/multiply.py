@@ -19,8 +19,8 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .views import (csc_view, csr_view, get_scaling_factor, get_ultimate_base, index_type,
-                    is_conjugated, value_type, _check_1d_cuda)
+from .views import (csc_view, csr_view, get_scaling_factor, get_ultimate_base, has_matrix_opt,
+                    index_type, is_conjugated, value_type, _check_1d_cuda)
 
 _NP = {_cabi.F32: np.float32, _cabi.F64: np.float64, _cabi.S32: np.int32}
 
@@ -206,6 +206,14 @@ def _inspect(info: operation_info_t, a, x, y, flags=_cabi.INSPECT_DEFAULT):
             plan, fmt, a_base.shape[0], a_base.shape[1], a_base.nnz, ptr.data_ptr(),
             ind.data_ptr(), index_type(ptr), index_type(ind), k_hint, flags)
     _cabi.raise_for_status(st, info._err())
+    if has_matrix_opt(a) and fmt == _cabi.CSC and flags == _cabi.INSPECT_DEFAULT:
+        # matrix_opt: the backend may keep optimised, value-dependent state (the reference's
+        # oneMKL backend calls optimize_gemv under the same condition) — here the values
+        # gathered once into the order of the row-major image
+        with torch.cuda.device(dev):
+            st = _cabi.lib().spblas_b200_plan_cache_values(plan, value_type(a_base.values),
+                                                           a_base.values.data_ptr())
+        _cabi.raise_for_status(st, info._err())
     info._sig = _signature(fmt, a_base, ptr, ind)
     info.result_shape = tuple(y.shape) if _is_matrix(y) else (int(y.shape[0]), 1)
     info.result_nnz = int(y.numel())

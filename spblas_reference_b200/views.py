@@ -99,7 +99,11 @@ class conjugated_view:
 @dataclass
 class matrix_opt:
     """Transparent wrapper; the reference uses it to carry a vendor handle
-    (views/matrix_opt_impl.hpp:88-92).  The b200 plan lives in operation_info_t."""
+    (views/matrix_opt_impl.hpp:88-92) and its oneMKL backend optimises only operands
+    wrapped in it (vendor/onemkl_sycl/spmv_impl.hpp:46-58).  Here the plan lives in
+    operation_info_t; multiply_inspect on a matrix_opt additionally lets the plan keep
+    value-dependent state (the values of a CSC / transposed operand gathered into image
+    order): the values must then stay unchanged until the next multiply_inspect."""
     base: Any
 
 
@@ -139,6 +143,15 @@ def get_scaling_factor(*tensors) -> Optional[Any]:
                 out = t.alpha if out is None else out * t.alpha
             t = t.base
     return out
+
+
+def has_matrix_opt(t) -> bool:
+    """detail/view_inspectors.hpp:113-122"""
+    while isinstance(t, (scaled_view, conjugated_view, matrix_opt)):
+        if isinstance(t, matrix_opt):
+            return True
+        t = t.base
+    return False
 
 
 def is_conjugated(t) -> bool:

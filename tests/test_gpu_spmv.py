@@ -342,3 +342,51 @@ def test_spmv_every_kernel_variant(cuda, oracle, monkeypatch, kind, variant, ws_
     assert_rows_within_bound(yc, oracle.spmv("csc", (m, n), cp, ri, v, x), t_rp,
                              oracle.abs_rowsum(t_rp, t_ci, v[perm], x), f"csc variant {variant}")
     info.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_matrix_opt_caches_values_of_a_transposed_operand(cuda, oracle, monkeypatch, variant):
+    """multiply_inspect(matrix_opt(transposed(a))) lets the plan keep the values gathered in
+    image order (spblas_b200_plan_cache_values): executes are bit-identical to the uncached
+    path; as with the reference's oneMKL optimize, changed values are only seen after the
+    next multiply_inspect; an operand without matrix_opt is never cached."""
+    monkeypatch.setenv("SPBLAS_B200_SPMV_VARIANT", str(variant))
+    rng = np.random.default_rng(31 + variant)
+    m, n = 2777, 3501
+    v, rp, ci, _ = _random_csr(rng, m, n, "mixed", np.float64, np.int32, np.int32)
+    x = rng.standard_normal(m)
+    a = csr_on_device(v, rp, ci, (m, n))
+    at = sb.transposed(a)                                       # n x m, CSC over A's arrays
+    xd = dev(x)
+    y_plain = torch.empty(n, dtype=torch.float64, device="cuda")
+    info_plain = sb.multiply_inspect(at, xd, y_plain)
+    sb.multiply_execute(info_plain, sb.scaled(0.5, at), xd, y_plain)
+    y_opt = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+    aopt = sb.matrix_opt(at)
+    info = sb.multiply_inspect(aopt, xd, y_opt)
+    sb.multiply_execute(info, sb.scaled(0.5, aopt), xd, y_opt)
+    torch.cuda.synchronize()
+    assert torch.equal(y_plain, y_opt)
+    t_rp, t_ci, perm = oracle.csc_row_major_image((n, m), rp, ci)
+    y_ref = oracle.spmv("csc", (n, m), rp, ci, v, x, alpha_a=0.5)
+    assert_rows_within_bound(y_opt.cpu().numpy(), y_ref, t_rp,
+                             oracle.abs_rowsum(t_rp, t_ci, v[perm], x, 0.5), "matrix_opt transposed")
+    # SpMM through the same cached plan state
+    B = rng.standard_normal((m, 8))
+    C1, C2 = (torch.empty((n, 8), dtype=torch.float64, device="cuda") for _ in range(2))
+    i1, i2 = sb.multiply_inspect(at, dev(B), C1), sb.multiply_inspect(aopt, dev(B), C2)
+    sb.multiply(i1, at, dev(B), C1)
+    sb.multiply(i2, aopt, dev(B), C2)
+    assert torch.equal(C1, C2)
+    # new values: the plain plan follows at once, the optimised one after re-inspection
+    v2 = rng.standard_normal(len(v))
+    a.values.copy_(dev(v2))
+    sb.multiply_execute(info_plain, at, xd, y_plain)
+    sb.multiply_inspect(info, aopt, xd, y_opt)
+    sb.multiply_execute(info, aopt, xd, y_opt)
+    torch.cuda.synchronize()
+    assert torch.equal(y_plain, y_opt)
+    assert_rows_within_bound(y_opt.cpu().numpy(), oracle.spmv("csc", (n, m), rp, ci, v2, x), t_rp,
+                             oracle.abs_rowsum(t_rp, t_ci, v2[perm], x), "matrix_opt re-inspected")
+    for i in (info_plain, info, i1, i2):
+        i.close()
