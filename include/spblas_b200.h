@@ -100,7 +100,9 @@ enum {
   SPBLAS_B200_Q_TILE_UNIFORM = 15,  /* int32[num_tiles]: common length L (1..8) of a tile's
                                        complete rows after the first, 0 if they differ          */
   SPBLAS_B200_Q_BARRIER_EPOCH = 16, /* int64[1]: fused-exchange steps signalled so far         */
-  SPBLAS_B200_Q_BARRIER_TIMEOUT = 17 /* int64[1]: 1 if a fused barrier gave up waiting for a peer */
+  SPBLAS_B200_Q_BARRIER_TIMEOUT = 17, /* int64[1]: 1 if a fused barrier gave up waiting for a peer */
+  SPBLAS_B200_Q_TRSV_LEVELS = 18,   /* int64[1]: level sets of the inspected triangular solve      */
+  SPBLAS_B200_Q_TRSV_SWEEPS = 19    /* int64[1]: relaxation sweeps the level analysis took          */
 };
 
 /* most destinations / peers of a fused exchange (one NVSwitch domain: 8 GPUs) */
@@ -207,6 +209,29 @@ SPBLAS_B200_API int spblas_b200_spmm_once(
     const void* d_ptr, const void* d_ind, int off_type, int idx_type,
     int val_type, const void* alpha, const void* d_values, const void* d_B,
     int64_t ldb, void* d_C, int64_t ldc, int64_t k);
+
+/* ---- triangular_solve(a, uplo, diag, b, x): x = inv(tri(A)) b -----------------
+
+   Replaces triangular_solve_inspect / triangular_solve
+   (algorithms/triangular_solve.hpp:8-19, algorithms/triangular_solve_impl.hpp:14-107: a
+   no-op inspect and a serial substitution).  A is a general square CSR matrix (m x m);
+   only the entries of the chosen triangle and — unless unit_diagonal — the diagonal
+   entries are used, the other triangle is ignored, exactly as the reference does.
+     trsv_inspect: level sets of the dependency graph, rows ordered by level; with an
+       explicit diagonal every row must store one (INVALID_STRUCTURE otherwise: the
+       reference divides by the previous row's diagonal there).
+     trsv: one launch per level, each x_i computed with the reference's operations in
+       the reference's order, every one rounded separately: bit-identical results.
+       alpha_a / alpha_b (HOST pointers, NULL = absent) are the factors of scaled(alpha, a)
+       and scaled(alpha, b), applied per element as the reference's views do.  d_b may
+       alias d_x.  f32 and f64 values. */
+SPBLAS_B200_API int spblas_b200_trsv_inspect(spblas_b200_plan* plan, int64_t m, int64_t nnz,
+                                             const void* d_rowptr, const void* d_colind,
+                                             int off_type, int idx_type, int upper,
+                                             int unit_diagonal);
+SPBLAS_B200_API int spblas_b200_trsv(spblas_b200_plan* plan, int val_type,
+                                     const void* alpha_a, const void* alpha_b,
+                                     const void* d_values, const void* d_b, void* d_x);
 
 /* ---- transpose(a, b): B = A^T, both CSR ---------------------------------------
 

@@ -208,6 +208,46 @@ def csc_row_major_image(shape, colptr, rowind):
     return t_rowptr, t_colind[:nnz], perm[:nnz]
 
 
+def trsv(m, rowptr, colind, values, b, upper=False, unit=False, alpha_a=None, alpha_b=None,
+         impl="oracle", x0=None):
+    """x = inv(tri(A)) b following reference algorithms/triangular_solve_impl.hpp:44-94
+    (A: general square CSR; only the chosen triangle and, with an explicit diagonal, the
+    diagonal entries are used).  alpha_a / alpha_b model scaled(alpha, a) / scaled(alpha, b).
+    x0: initial contents of x (the reference reads x only at already solved positions)."""
+    rowptr, colind, values, b = _c(rowptr), _c(colind), _c(values), _c(b)
+    tn, inn, on = _names(values, colind, rowptr)
+    assert b.dtype == values.dtype and b.shape == (m,)
+    x = np.full(m, np.nan, dtype=values.dtype) if x0 is None else _c(x0).copy()
+    args = (_p(rowptr), _p(colind), _p(values), C.c_int(int(upper)), C.c_int(int(unit)),
+            C.c_int(alpha_a is not None), _scal(tn, alpha_a), C.c_int(alpha_b is not None),
+            _scal(tn, alpha_b), _p(b), _p(x))
+    if impl == "oracle":
+        fn = getattr(lib(), f"oracle_csr_trsv_{tn}_{inn}_{on}")
+        fn.restype = None
+        fn(C.c_int64(m), *args)
+    else:
+        fn = getattr(ref(), f"ref_csr_trsv_{tn}_{inn}_{on}")
+        fn.restype = None
+        nnz = int(rowptr[-1] - rowptr[0]) if len(rowptr) else 0
+        fn(C.c_int64(m), C.c_int64(nnz), *args)
+    return x
+
+
+def trsv_levels(m, rowptr, colind, upper=False):
+    """Level of every row in the dependency graph of the chosen triangle: 0 for a row
+    whose solve needs no other unknown, else 1 + the largest level among the unknowns it
+    reads (definition used by csrc/trsv.cu; plain restatement, small cases only)."""
+    rowptr, colind = _c(rowptr, np.int64), _c(colind, np.int64)
+    level = np.zeros(m, dtype=np.int64)
+    rows = range(m - 1, -1, -1) if upper else range(m)
+    for i in rows:
+        ks = colind[rowptr[i]:rowptr[i + 1]]
+        deps = ks[ks > i] if upper else ks[ks < i]
+        if len(deps):
+            level[i] = level[deps].max() + 1
+    return level
+
+
 def transpose(shape, rowptr, colind, values, impl="oracle"):
     """B = A^T as CSR following reference algorithms/transpose_impl.hpp:14-53.
     Returns (b_values, b_rowptr, b_colind) with the dtypes of the inputs."""

@@ -135,6 +135,51 @@ void spmm(A a, int has_aa, T alpha_a, int has_ab, T alpha_b, const T* B,
     spblas::transpose(info, a, b);                                                 \
   }
 
+// triangular_solve_inspect + triangular_solve as examples/sptrsv_csr.cpp:52-56 spells them
+template <typename A, typename T>
+void trsv(A a, int upper, int unit, int has_aa, T alpha_a, int has_ab, T alpha_b,
+          const T* b, T* x, int64_t m) {
+  std::span<T> bs(const_cast<T*>(b), size_t(m));
+  std::span<T> xs(x, size_t(m));
+  auto run2 = [&](auto&& av, auto&& bv) {
+    auto go = [&](auto uplo, auto diag) {
+      auto info = spblas::triangular_solve_inspect(av, uplo, diag, bv, xs);
+      spblas::triangular_solve(info, av, uplo, diag, bv, xs);
+    };
+    if (upper && unit)
+      go(spblas::upper_triangle_t{}, spblas::implicit_unit_diagonal_t{});
+    else if (upper)
+      go(spblas::upper_triangle_t{}, spblas::explicit_diagonal_t{});
+    else if (unit)
+      go(spblas::lower_triangle_t{}, spblas::implicit_unit_diagonal_t{});
+    else
+      go(spblas::lower_triangle_t{}, spblas::explicit_diagonal_t{});
+  };
+  if (has_aa && has_ab)
+    run2(spblas::scaled(alpha_a, a), spblas::scaled(alpha_b, bs));
+  else if (has_aa)
+    run2(spblas::scaled(alpha_a, a), bs);
+  else if (has_ab)
+    run2(a, spblas::scaled(alpha_b, bs));
+  else
+    run2(a, bs);
+}
+
+#define DEF_TRSV(T, TN, I, IN, O, ON)                                              \
+  REF_API void ref_csr_trsv_##TN##_##IN##_##ON(                                    \
+      int64_t m, int64_t nnz, const O* rowptr, const I* colind, const T* values,   \
+      int upper, int unit, int has_aa, T alpha_a, int has_ab, T alpha_b,           \
+      const T* b, T* x) {                                                          \
+    trsv(make_csr<T, I, O>(m, m, nnz, rowptr, colind, values), upper, unit,        \
+         has_aa, alpha_a, has_ab, alpha_b, b, x, m);                               \
+  }
+
+DEF_TRSV(float, f32, int32_t, i32, int32_t, i32)
+DEF_TRSV(float, f32, int32_t, i32, int64_t, i64)
+DEF_TRSV(double, f64, int32_t, i32, int32_t, i32)
+DEF_TRSV(double, f64, int32_t, i32, int64_t, i64)
+DEF_TRSV(float, f32, int64_t, i64, int64_t, i64)
+
 DEF_TRANSPOSE(float, f32, int32_t, i32, int32_t, i32)
 DEF_TRANSPOSE(float, f32, int32_t, i32, int64_t, i64)
 DEF_TRANSPOSE(double, f64, int32_t, i32, int32_t, i32)

@@ -11,12 +11,16 @@ from . import _cabi
 from .multiply import (multiply, multiply_execute, multiply_execute_host, multiply_inspect,
                        operation_info_t)
 from .transpose import transpose, transpose_inspect
+from .triangular_solve import (explicit_diagonal, implicit_unit_diagonal, lower_triangle,
+                               triangular_solve, triangular_solve_inspect, upper_triangle)
 from .views import (conjugated, csc_view, csr_view, matrix_opt, scaled, scaled_view,
                     transposed)
 
 __all__ = [
     "multiply", "multiply_inspect", "multiply_execute", "multiply_execute_host",
     "operation_info_t", "transpose", "transpose_inspect",
+    "triangular_solve", "triangular_solve_inspect", "lower_triangle", "upper_triangle",
+    "explicit_diagonal", "implicit_unit_diagonal",
     "csr_view", "csc_view", "scaled", "scaled_view", "transposed", "matrix_opt",
     "conjugated",
 ]

@@ -23,7 +23,7 @@ INSPECT_DEFAULT, INSPECT_LIGHT = 0, 1
 (Q_NUM_TILES, Q_TILE_ITEMS, Q_TILE_STARTS, Q_ROWLEN_HIST, Q_MAX_ROW_LEN, Q_EMPTY_ROWS,
  Q_SPMV_VARIANT, Q_LAST_LAUNCHES, Q_TOTAL_LAUNCHES, Q_CSR_ROWPTR, Q_CSR_COLIND,
  Q_CSR_PERM, Q_NUM_SEGMENTS, Q_SEGMENTS, Q_SPMM_VARIANT, Q_TILE_UNIFORM,
- Q_BARRIER_EPOCH, Q_BARRIER_TIMEOUT) = range(18)
+ Q_BARRIER_EPOCH, Q_BARRIER_TIMEOUT, Q_TRSV_LEVELS, Q_TRSV_SWEEPS) = range(20)
 MAX_PEERS = 8
 HIST_BINS = 40
 
@@ -38,7 +38,7 @@ SYMBOLS = (
     "spblas_b200_plan_set_scatter", "spblas_b200_plan_set_barrier",
     "spblas_b200_spmv_host", "spblas_b200_probe_gather",
     "spblas_b200_transpose_inspect", "spblas_b200_transpose",
-    "spblas_b200_plan_cache_values",
+    "spblas_b200_plan_cache_values", "spblas_b200_trsv_inspect", "spblas_b200_trsv",
 )
 
 
@@ -86,6 +86,10 @@ def lib() -> C.CDLL:
     L.spblas_b200_spmv.restype = i32
     L.spblas_b200_spmv_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.spblas_b200_spmv_host.restype = i32
+    L.spblas_b200_trsv_inspect.argtypes = [vp, i64, i64, vp, vp, i32, i32, i32, i32]
+    L.spblas_b200_trsv_inspect.restype = i32
+    L.spblas_b200_trsv.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.spblas_b200_trsv.restype = i32
     L.spblas_b200_plan_cache_values.argtypes = [vp, i32, vp]
     L.spblas_b200_plan_cache_values.restype = i32
     L.spblas_b200_transpose_inspect.argtypes = [vp, i64, i64, i64, vp, vp, i32, i32]

@@ -65,7 +65,9 @@ void release_all(spblas_b200_plan* p) {
                           &p->carry_val,   &p->segments,   &p->seg_partial,
                           &p->seg_counter, &p->stats,      &p->spmm_starts,
                           &p->spmm_carry_row, &p->spmm_carry_val, &p->barrier_state,
-                          &p->ws_starts, &p->ws_carry_row, &p->ws_carry_val, &p->own_values};
+                          &p->ws_starts, &p->ws_carry_row, &p->ws_carry_val, &p->own_values,
+                          &p->trsv_level, &p->trsv_order, &p->trsv_tmp0, &p->trsv_tmp1,
+                          &p->trsv_level_ptr};
   for (DeviceBuffer* b : bufs)
     release(*b);
   release(p->hc_colmax);
@@ -356,6 +358,51 @@ int spblas_b200_plan_cache_values(spblas_b200_plan* p, int val_type, const void*
   return SPBLAS_B200_SUCCESS;
 }
 
+int spblas_b200_trsv_inspect(spblas_b200_plan* p, int64_t m, int64_t nnz,
+                             const void* d_rowptr, const void* d_colind, int off_type,
+                             int idx_type, int upper, int unit_diagonal) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  p->trsv_ready = false;
+  if (!valid_index_type(off_type) || !valid_index_type(idx_type))
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "index/offset type must be int32 or int64");
+  if (m < 0 || nnz < 0)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "negative dimension");
+  if (m > 0x7fffffff)
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "triangular_solve supports at most 2^31-1 rows");
+  if (m > 0 && !d_rowptr)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "offsets pointer is null");
+  if (nnz > 0 && !d_colind)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "indices pointer is null");
+  p->off_type = off_type;
+  p->idx_type = idx_type;
+  p->trsv_upper = upper ? 1 : 0;
+  p->trsv_unit = unit_diagonal ? 1 : 0;
+  p->trsv_m = m;
+  p->trsv_rowptr = d_rowptr;
+  p->trsv_colind = d_colind;
+  // the plan now describes a triangular solve, not a product
+  p->inspected = false;
+  const int rc = trsv_inspect(p, m, d_rowptr, d_colind, p->trsv_upper, p->trsv_unit);
+  if (rc == SPBLAS_B200_SUCCESS)
+    p->trsv_ready = true;
+  return rc;
+}
+
+int spblas_b200_trsv(spblas_b200_plan* p, int val_type, const void* alpha_a,
+                     const void* alpha_b, const void* d_values, const void* d_b,
+                     void* d_x) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  if (!p->trsv_ready)
+    return fail(p, SPBLAS_B200_NOT_INSPECTED, "trsv called before trsv_inspect");
+  if (p->trsv_m > 0 && (!d_b || !d_x || !d_values))
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null device pointer");
+  return trsv_solve(p, val_type, alpha_a, alpha_b, d_values, d_b, d_x);
+}
+
 int spblas_b200_transpose_inspect(spblas_b200_plan* p, int64_t m, int64_t n, int64_t nnz,
                                   const void* d_rowptr, const void* d_colind,
                                   int off_type, int idx_type) {
@@ -531,6 +578,10 @@ int spblas_b200_plan_query(spblas_b200_plan* p, int what, void* out,
     }
     return scalar(int64_t(st[1]));
   }
+  case SPBLAS_B200_Q_TRSV_LEVELS:
+    return scalar(p->trsv_ready ? p->trsv_levels : 0);
+  case SPBLAS_B200_Q_TRSV_SWEEPS:
+    return scalar(p->trsv_ready ? p->trsv_sweeps : 0);
   case SPBLAS_B200_Q_LAST_LAUNCHES:
     return scalar(p->last_launches);
   case SPBLAS_B200_Q_TOTAL_LAUNCHES:

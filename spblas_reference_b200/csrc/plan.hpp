@@ -108,6 +108,18 @@ struct spblas_b200_plan {
   const void* cached_src = nullptr;
   b200::DeviceBuffer own_values;
 
+  // ---- triangular solve (trsv.cu): level sets of the inspected triangle ---------------
+  bool trsv_ready = false;
+  int trsv_upper = 0, trsv_unit = 0;
+  int64_t trsv_m = 0, trsv_levels = 0, trsv_sweeps = 0;
+  const void* trsv_rowptr = nullptr;
+  const void* trsv_colind = nullptr;
+  b200::DeviceBuffer trsv_level;     // int32 per row
+  b200::DeviceBuffer trsv_order;     // int32 row ids, ascending level
+  b200::DeviceBuffer trsv_tmp0, trsv_tmp1;
+  b200::DeviceBuffer trsv_level_ptr; // int64 offsets of the levels in trsv_order
+  std::vector<int64_t> trsv_level_ptr_h;
+
   // ---- merge-path partition --------------------------------------------------
   int tile_items = b200::kSpmvTileItems;
   int tile_items_override = 0; // env SPBLAS_B200_TILE_ITEMS (tuning)
@@ -221,6 +233,11 @@ int run_spmv_host(spblas_b200_plan* p, int val_type, const void* alpha,
                   const void* values, const void* h_x, void* h_y, void* d_x,
                   void* d_y);
 void release_host_exec(spblas_b200_plan* p);
+// trsv.cu
+int trsv_inspect(spblas_b200_plan* p, int64_t m, const void* d_rowptr, const void* d_colind,
+                 int upper, int unit);
+int trsv_solve(spblas_b200_plan* p, int val_type, const void* alpha_a, const void* alpha_b,
+               const void* values, const void* b, void* x);
 // spmm.cu
 int run_spmm(spblas_b200_plan* p, int val_type, const void* alpha,
              const void* values, const void* B, int64_t ldb, void* C,

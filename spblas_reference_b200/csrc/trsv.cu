@@ -1,0 +1,297 @@
+// trsv.cu — x = inv(tri(A)) b for a square CSR matrix A (SpTRSV), level-scheduled.
+//
+// Replaces the reference's serial substitution
+// (include/spblas/algorithms/triangular_solve_impl.hpp:44-94: rows in solve order, per
+// row one pass over the stored entries in storage order — entries on the dependency
+// side of the diagonal go into dot_product, an entry on the diagonal sets
+// diagonal_value, the other side is ignored — then x_i = (b_i - dot) / diagonal_value,
+// or b_i - dot with implicit_unit_diagonal_t) and the no-op triangular_solve_inspect
+// (:14-41).
+//
+// Inspect (GPU): level[i] = 1 + max level of the rows x_i depends on (0 if none), by
+// monotone relaxation sweeps until nothing changes; rows ordered by level with a
+// stable radix sort (cub, inspect only); offsets of the levels; with an explicit
+// diagonal, a check that every row stores one (the reference would divide by the
+// PREVIOUS row's diagonal there — diagonal_value is declared outside its row loop,
+// :59 — which no parallel schedule can or should reproduce: it is an inspect error
+// here).
+//
+// Execute: one launch per level over that level's rows, one thread per row, entries in
+// storage order, every operation rounded separately (__fmul_rn / __fadd_rn / ... : no
+// FMA contraction), so that each x_i goes through exactly the arithmetic of the
+// reference's loop: the result is BIT-IDENTICAL to the reference's (the oracle and the
+// real reference are compiled with -ffp-contract=off), not merely close.  Rows of one
+// level never depend on each other, and a launch boundary orders the levels: no flags,
+// no spinning, nothing that can hang.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "device_utils.cuh"
+#include "plan.hpp"
+
+namespace b200 {
+
+namespace {
+
+template <typename I, typename O>
+__global__ void __launch_bounds__(256)
+trsv_relax_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind, int64_t m,
+                  int upper, int* __restrict__ level, int* __restrict__ changed,
+                  unsigned long long* __restrict__ max_level) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < m; t += stride) {
+    // sweep in solve order so that one sweep carries a level as far as it can
+    const int64_t i = upper ? m - 1 - t : t;
+    int lvl = 0;
+    for (O p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+      const int64_t k = int64_t(colind[p]);
+      if (upper ? k > i : k < i) {
+        const int lk = reinterpret_cast<volatile int*>(level)[k] + 1;
+        lvl = lk > lvl ? lk : lvl;
+      }
+    }
+    if (lvl > level[i]) {
+      level[i] = lvl;
+      *changed = 1;
+      atomicMax(max_level, (unsigned long long)lvl);
+    }
+  }
+}
+
+// stats[1] = rows without a stored diagonal, stats[2] = rows with a column index outside
+// [0, m); also fills the identity permutation the sort will carry
+template <typename I, typename O>
+__global__ void __launch_bounds__(256)
+trsv_check_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind, int64_t m,
+                  int* __restrict__ row_ids, unsigned long long* __restrict__ stats) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < m; i += stride) {
+    bool diag = false, bad = false;
+    for (O p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+      const int64_t k = int64_t(colind[p]);
+      diag = diag || k == i;
+      bad = bad || k < 0 || k >= m;
+    }
+    row_ids[i] = int(i);
+    if (!diag)
+      atomicAdd(&stats[1], 1ull);
+    if (bad)
+      atomicAdd(&stats[2], 1ull);
+  }
+}
+
+// out[l] = first position in the sorted level array whose level is >= l
+__global__ void __launch_bounds__(256)
+trsv_level_ptr_kernel(const int* __restrict__ sorted_level, int64_t m, int64_t nlevels,
+                      int64_t* __restrict__ out) {
+  const int64_t l = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (l > nlevels)
+    return;
+  int64_t lo = 0, hi = m;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (int64_t(sorted_level[mid]) < l)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  out[l] = lo;
+}
+
+// every operation rounded on its own, as the reference's scalar loop compiled without
+// contraction does
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+template <typename T, typename I, typename O>
+__global__ void __launch_bounds__(128)
+trsv_level_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
+                  const T* __restrict__ values, const int* __restrict__ rows, int64_t nrows,
+                  int upper, int unit, int has_aa, T alpha_a, int has_ab, T alpha_b,
+                  const T* b, T* x) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= nrows)
+    return;
+  const int64_t i = rows[t];
+  T dot = T(0), diag = T(0);
+  for (O p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+    const int64_t k = int64_t(colind[p]);
+    T a_v = values[p];
+    if (has_aa)
+      a_v = mul_rn(alpha_a, a_v);
+    if (upper ? k > i : k < i)
+      dot = add_rn(dot, mul_rn(a_v, x[k])); // x[k]: written by an earlier launch
+    else if (k == i)
+      diag = a_v; // the last stored diagonal entry wins, as in the reference
+  }
+  T b_i = b[i];
+  if (has_ab)
+    b_i = mul_rn(alpha_b, b_i);
+  const T num = sub_rn(b_i, dot);
+  x[i] = unit ? num : div_rn(num, diag);
+}
+
+int check(spblas_b200_plan* p, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? SPBLAS_B200_SUCCESS : cuda_fail(p, e, what);
+}
+
+template <typename I, typename O>
+int trsv_inspect_typed(spblas_b200_plan* p, int64_t m, const void* d_rowptr,
+                       const void* d_colind, int upper, int unit) {
+  cudaStream_t s = p->stream;
+  const O* rowptr = static_cast<const O*>(d_rowptr);
+  const I* colind = static_cast<const I*>(d_colind);
+  if (int rc = reserve(p, p->trsv_level, size_t(std::max<int64_t>(m, 1)) * sizeof(int)))
+    return rc;
+  if (int rc = reserve(p, p->trsv_order, size_t(std::max<int64_t>(m, 1)) * sizeof(int)))
+    return rc;
+  if (int rc = reserve(p, p->trsv_tmp0, size_t(std::max<int64_t>(m, 1)) * sizeof(int)))
+    return rc;
+  if (int rc = reserve(p, p->trsv_tmp1, size_t(std::max<int64_t>(m, 1)) * sizeof(int)))
+    return rc;
+  if (int rc = reserve(p, p->stats, 64 * sizeof(unsigned long long)))
+    return rc;
+  int* level = static_cast<int*>(p->trsv_level.p);
+  int* order = static_cast<int*>(p->trsv_order.p);
+  int* row_ids = static_cast<int*>(p->trsv_tmp0.p);
+  int* sorted_level = static_cast<int*>(p->trsv_tmp1.p);
+  unsigned long long* stats = static_cast<unsigned long long*>(p->stats.p);
+  int* changed = reinterpret_cast<int*>(stats + 8);
+  p->trsv_level_ptr_h.assign(1, 0);
+  p->trsv_levels = 0;
+  if (m == 0)
+    return SPBLAS_B200_SUCCESS;
+
+  B200_CUDA_TRY(p, cudaMemsetAsync(level, 0, size_t(m) * sizeof(int), s));
+  B200_CUDA_TRY(p, cudaMemsetAsync(stats, 0, 16 * sizeof(unsigned long long), s));
+  const int grid = int(std::min<int64_t>((m + 255) / 256, int64_t(p->num_sms) * 16));
+  // structure first: the sweeps below index level[] with the column indices
+  trsv_check_kernel<I, O><<<grid, 256, 0, s>>>(rowptr, colind, m, row_ids, stats);
+  if (int rc = check(p, "trsv_check_kernel"))
+    return rc;
+  unsigned long long h_stats[3] = {0, 0, 0};
+  B200_CUDA_TRY(p, cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, s));
+  B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+  if (h_stats[2] > 0)
+    return fail(p, SPBLAS_B200_INVALID_STRUCTURE, "column index outside the matrix");
+  if (!unit && h_stats[1] > 0)
+    return fail(p, SPBLAS_B200_INVALID_STRUCTURE,
+                "explicit_diagonal: " + std::to_string(h_stats[1]) +
+                    " row(s) store no diagonal entry");
+  // relaxation sweeps: a level can only grow, and it is final once a sweep changes nothing
+  for (int64_t sweep = 0;; ++sweep) {
+    if (sweep > m)
+      return fail(p, SPBLAS_B200_INVALID_STRUCTURE, "level analysis did not converge");
+    B200_CUDA_TRY(p, cudaMemsetAsync(changed, 0, sizeof(int), s));
+    trsv_relax_kernel<I, O><<<grid, 256, 0, s>>>(rowptr, colind, m, upper, level, changed,
+                                                 stats);
+    if (int rc = check(p, "trsv_relax_kernel"))
+      return rc;
+    int h_changed = 0;
+    B200_CUDA_TRY(p, cudaMemcpyAsync(&h_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+    p->trsv_sweeps = sweep + 1;
+    if (!h_changed)
+      break;
+  }
+  B200_CUDA_TRY(p, cudaMemcpyAsync(h_stats, stats, sizeof(h_stats[0]), cudaMemcpyDeviceToHost, s));
+  B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+  const int64_t nlevels = int64_t(h_stats[0]) + 1;
+  int end_bit = 1;
+  while (end_bit < 31 && (int64_t(1) << end_bit) < nlevels)
+    ++end_bit;
+  size_t ws_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, ws_bytes, level, sorted_level, row_ids, order,
+                                  int(m), 0, end_bit, s);
+  if (int rc = reserve(p, p->sort_ws, ws_bytes))
+    return rc;
+  B200_CUDA_TRY(p, cub::DeviceRadixSort::SortPairs(p->sort_ws.p, ws_bytes, level, sorted_level,
+                                                   row_ids, order, int(m), 0, end_bit, s));
+  if (int rc = reserve(p, p->trsv_level_ptr, size_t(nlevels + 1) * sizeof(int64_t)))
+    return rc;
+  trsv_level_ptr_kernel<<<int((nlevels + 1 + 255) / 256), 256, 0, s>>>(
+      sorted_level, m, nlevels, static_cast<int64_t*>(p->trsv_level_ptr.p));
+  if (int rc = check(p, "trsv_level_ptr_kernel"))
+    return rc;
+  p->trsv_level_ptr_h.assign(size_t(nlevels + 1), 0);
+  B200_CUDA_TRY(p, cudaMemcpyAsync(p->trsv_level_ptr_h.data(), p->trsv_level_ptr.p,
+                                   size_t(nlevels + 1) * sizeof(int64_t),
+                                   cudaMemcpyDeviceToHost, s));
+  B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+  p->trsv_levels = nlevels;
+  return SPBLAS_B200_SUCCESS;
+}
+
+template <typename T, typename I, typename O>
+int trsv_solve_typed(spblas_b200_plan* p, const void* alpha_a, const void* alpha_b,
+                     const void* values, const void* b, void* x) {
+  const T aa = alpha_a ? *static_cast<const T*>(alpha_a) : T(1);
+  const T ab = alpha_b ? *static_cast<const T*>(alpha_b) : T(1);
+  const int* order = static_cast<const int*>(p->trsv_order.p);
+  int launches = 0;
+  for (int64_t l = 0; l < p->trsv_levels; ++l) {
+    const int64_t r0 = p->trsv_level_ptr_h[size_t(l)], r1 = p->trsv_level_ptr_h[size_t(l) + 1];
+    if (r1 <= r0)
+      continue;
+    const int64_t nrows = r1 - r0;
+    trsv_level_kernel<T, I, O><<<unsigned((nrows + 127) / 128), 128, 0, p->stream>>>(
+        static_cast<const O*>(p->trsv_rowptr), static_cast<const I*>(p->trsv_colind),
+        static_cast<const T*>(values), order + r0, nrows, p->trsv_upper, p->trsv_unit,
+        alpha_a != nullptr, aa, alpha_b != nullptr, ab, static_cast<const T*>(b),
+        static_cast<T*>(x));
+    ++launches;
+  }
+  if (int rc = check(p, "trsv_level_kernel"))
+    return rc;
+  p->last_launches = launches;
+  p->total_launches += launches;
+  return SPBLAS_B200_SUCCESS;
+}
+
+} // namespace
+
+int trsv_inspect(spblas_b200_plan* p, int64_t m, const void* d_rowptr, const void* d_colind,
+                 int upper, int unit) {
+  const bool i64 = p->idx_type == SPBLAS_B200_I64, o64 = p->off_type == SPBLAS_B200_I64;
+  if (!i64 && !o64)
+    return trsv_inspect_typed<int32_t, int32_t>(p, m, d_rowptr, d_colind, upper, unit);
+  if (!i64 && o64)
+    return trsv_inspect_typed<int32_t, int64_t>(p, m, d_rowptr, d_colind, upper, unit);
+  if (i64 && !o64)
+    return trsv_inspect_typed<int64_t, int32_t>(p, m, d_rowptr, d_colind, upper, unit);
+  return trsv_inspect_typed<int64_t, int64_t>(p, m, d_rowptr, d_colind, upper, unit);
+}
+
+template <typename T>
+static int trsv_dispatch(spblas_b200_plan* p, const void* alpha_a, const void* alpha_b,
+                         const void* values, const void* b, void* x) {
+  const bool i64 = p->idx_type == SPBLAS_B200_I64, o64 = p->off_type == SPBLAS_B200_I64;
+  if (!i64 && !o64)
+    return trsv_solve_typed<T, int32_t, int32_t>(p, alpha_a, alpha_b, values, b, x);
+  if (!i64 && o64)
+    return trsv_solve_typed<T, int32_t, int64_t>(p, alpha_a, alpha_b, values, b, x);
+  if (i64 && !o64)
+    return trsv_solve_typed<T, int64_t, int32_t>(p, alpha_a, alpha_b, values, b, x);
+  return trsv_solve_typed<T, int64_t, int64_t>(p, alpha_a, alpha_b, values, b, x);
+}
+
+int trsv_solve(spblas_b200_plan* p, int val_type, const void* alpha_a, const void* alpha_b,
+               const void* values, const void* b, void* x) {
+  p->last_launches = 0;
+  if (val_type == SPBLAS_B200_F32)
+    return trsv_dispatch<float>(p, alpha_a, alpha_b, values, b, x);
+  if (val_type == SPBLAS_B200_F64)
+    return trsv_dispatch<double>(p, alpha_a, alpha_b, values, b, x);
+  return fail(p, SPBLAS_B200_NOT_SUPPORTED, "triangular_solve needs f32 or f64 values");
+}
+
+} // namespace b200

@@ -112,6 +112,11 @@ class operation_info_t:
     def spmm_variant(self): return self._query_scalar(_cabi.Q_SPMM_VARIANT)
 
     @property
+    def trsv_levels(self): return self._query_scalar(_cabi.Q_TRSV_LEVELS)
+    @property
+    def trsv_sweeps(self): return self._query_scalar(_cabi.Q_TRSV_SWEEPS)
+
+    @property
     def barrier_epoch(self): return self._query_scalar(_cabi.Q_BARRIER_EPOCH)
     @property
     def barrier_timeout(self): return self._query_scalar(_cabi.Q_BARRIER_TIMEOUT)

@@ -381,6 +381,89 @@ void transpose_cases() {
   }
 }
 
+// ---- triangular_solve: the reference's host loop restated, results must be IDENTICAL -----------
+template <typename T, typename I, typename O, typename Triangle, typename Diag>
+void trsv_case(Triangle uplo, Diag diag) {
+  constexpr bool upper = std::is_same_v<Triangle, spblas::upper_triangle_t>;
+  constexpr bool unit = std::is_same_v<Diag, spblas::implicit_unit_diagonal_t>;
+  for (auto [m, n, nnz] : std::vector<std::tuple<int, int, int>>{
+           {1000, 1000, 100}, {100, 100, 100}, {40, 40, 1000}}) { // util::square_dims
+    auto [gv, grp, gci, shape, nnz_] = spblas::generate_csr<T, I, O>(m, n, nnz);
+    // put a diagonal entry in front of every row; off-diagonals scaled as the reference test does
+    std::vector<T> values;
+    std::vector<O> rowptr(m + 1, 0);
+    std::vector<I> colind;
+    for (int i = 0; i < m; ++i) {
+      colind.push_back(I(i));
+      values.push_back(T(2 + i % 3));
+      for (O p = grp[i]; p < grp[i + 1]; ++p) {
+        colind.push_back(gci[p]);
+        values.push_back(T(1e-3) * gv[p]);
+      }
+      rowptr[i + 1] = O(colind.size());
+    }
+    std::vector<T> b(m), x_ref(m, T(0));
+    for (int i = 0; i < m; ++i)
+      b[i] = T(1 + i % 7);
+    const T alpha = T(1.2);
+    T dval = 0;
+    for (int s = 0; s < m; ++s) {                 // algorithms/triangular_solve_impl.hpp:61-93
+      const int i = upper ? m - 1 - s : s;
+      T dot = 0;
+      for (O p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+        const int k = int(colind[p]);
+        if (upper ? k > i : k < i) {
+          volatile T prod = values[p] * x_ref[k]; // no contraction: multiply, then add
+          dot = dot + prod;
+        } else if (k == i) {
+          dval = values[p];
+        }
+      }
+      volatile T bi = alpha * b[i];
+      volatile T num = bi - dot;
+      x_ref[i] = unit ? T(num) : T(num / dval);
+    }
+    device_array<T> d_values(values), d_b(b), d_x(std::size_t(m), std::numeric_limits<T>::quiet_NaN());
+    device_array<O> d_rowptr(rowptr);
+    device_array<I> d_colind(colind);
+    spblas::csr_view<T, I, O> a(d_values.get(), d_rowptr.get(), d_colind.get(),
+                                spblas::index<I>(I(m), I(m)), O(colind.size()));
+    std::span<T> b_span(d_b.get(), m), x_span(d_x.get(), m);
+    g_case = "triangular_solve";
+    auto info = spblas::triangular_solve_inspect(a, uplo, diag, spblas::scaled(alpha, b_span), x_span);
+    spblas::triangular_solve(info, a, uplo, diag, spblas::scaled(alpha, b_span), x_span);
+    ++g_checks;
+    if (d_x.to_host() != x_ref)
+      fail("triangular_solve differs from the reference loop");
+    spblas::matrix_opt a_opt(a);
+    spblas::triangular_solve(a_opt, uplo, diag, spblas::scaled(alpha, b_span), x_span); // no info
+    ++g_checks;
+    if (d_x.to_host() != x_ref)
+      fail("triangular_solve (no info, matrix_opt) differs from the reference loop");
+  }
+}
+
+void trsv_errors() {
+  using T = float;
+  using I = spblas::index_t;
+  g_case = "triangular_solve errors";
+  std::vector<T> v{1, 1, 1};
+  std::vector<I> rp{0, 1, 2, 3}, ci{0, 0, 2};
+  device_array<T> d_v(v), d_b(std::size_t(3), T(1)), d_x(std::size_t(3), T(0));
+  device_array<I> d_rp(rp), d_ci(ci);
+  spblas::csr_view<T, I> a(d_v.get(), d_rp.get(), d_ci.get(), spblas::index<I>(3, 3), 3);
+  ++g_checks;
+  try {
+    spblas::triangular_solve(a, spblas::lower_triangle, spblas::explicit_diagonal,
+                             std::span<T>(d_b.get(), 3), std::span<T>(d_x.get(), 3));
+    fail("no exception for a row without a diagonal under explicit_diagonal");
+  } catch (const std::runtime_error&) {
+  }
+  spblas::triangular_solve(a, spblas::lower_triangle, spblas::implicit_unit_diagonal,
+                           std::span<T>(d_b.get(), 3), std::span<T>(d_x.get(), 3));
+  expect_all_close(std::vector<T>{1, 0, 1}, d_x.to_host());
+}
+
 // ---- error behaviour --------------------------------------------------------------------------
 void error_cases() {
   using T = float;
@@ -430,6 +513,11 @@ int main() {
   csc_spmm_case();
   transpose_cases<float, spblas::index_t, spblas::offset_t>();
   transpose_cases<double, std::int32_t, std::int64_t>();
+  trsv_case<float, spblas::index_t, spblas::offset_t>(spblas::lower_triangle, spblas::implicit_unit_diagonal);
+  trsv_case<float, spblas::index_t, spblas::offset_t>(spblas::upper_triangle, spblas::explicit_diagonal);
+  trsv_case<double, std::int32_t, std::int64_t>(spblas::lower_triangle, spblas::explicit_diagonal);
+  trsv_case<double, std::int32_t, std::int64_t>(spblas::upper_triangle, spblas::implicit_unit_diagonal);
+  trsv_errors();
   error_cases();
   std::printf("dropin_test: %d checks, %d failures\n", g_checks, g_failures);
   return g_failures == 0 ? 0 : 1;

@@ -57,6 +57,38 @@ def main():
         np.savez_compressed(path, **out)
         print(path, os.path.getsize(path) // 1024, "KiB")
 
+    # triangular_solve on the reference's own fixtures (test/gtest/triangular_solve_test.cpp:
+    # generate_csr over util::square_dims, values scaled by 1e-3) with b = 1, 2, 3, ... so that
+    # the answer is not trivially zero, both triangles, implicit unit diagonal; and with an
+    # explicit diagonal on the same matrices after a diagonal entry was put in front of every row
+    SQUARE_DIMS = [(1000, 1000, 100), (100, 100, 100), (40, 40, 1000)]   # util.hpp:31-33
+    out = {}
+    for (m, n, nnz) in SQUARE_DIMS:
+        values, ptr, ind = O.ref_generate_csr(m, n, nnz, 0, np.float32)
+        values = (np.float32(1e-3) * values).astype(np.float32)
+        b = (1 + np.arange(m) % 7).astype(np.float32)
+        key = f"{m}_{nnz}"
+        out[f"values_{key}"], out[f"ptr_{key}"], out[f"ind_{key}"], out[f"b_{key}"] = values, ptr, ind, b
+        for upper in (0, 1):
+            out[f"x_unit_{'upper' if upper else 'lower'}_{key}"] = O.trsv(
+                m, ptr, ind, values, b, upper=upper, unit=True, impl="reference")
+        lens = np.diff(ptr)
+        dptr = (ptr + np.arange(m + 1)).astype(np.int32)
+        dind = np.empty(len(ind) + m, np.int32)
+        dval = np.empty(len(ind) + m, np.float32)
+        for i in range(m):
+            dind[dptr[i]], dval[dptr[i]] = i, np.float32(2 + (i % 3))
+            dind[dptr[i] + 1:dptr[i + 1]] = ind[ptr[i]:ptr[i + 1]]
+            dval[dptr[i] + 1:dptr[i + 1]] = values[ptr[i]:ptr[i + 1]]
+        out[f"dvalues_{key}"], out[f"dptr_{key}"], out[f"dind_{key}"] = dval, dptr, dind
+        for upper in (0, 1):
+            out[f"x_explicit_{'upper' if upper else 'lower'}_{key}"] = O.trsv(
+                m, dptr, dind, dval, b, upper=upper, unit=False, impl="reference")
+            out[f"x_explicit_scaled_{'upper' if upper else 'lower'}_{key}"] = O.trsv(
+                m, dptr, dind, dval, b, upper=upper, unit=False, alpha_b=1.2, impl="reference")
+    np.savez_compressed(os.path.join(HERE, "trsv_square_dims.npz"), **out)
+    print("trsv_square_dims.npz", os.path.getsize(os.path.join(HERE, "trsv_square_dims.npz")) // 1024, "KiB")
+
     # the 3x4 probe of SURVEY.md Appendix A (unsorted row with a duplicate column, an
     # empty row, stale NaN in y, an unreferenced Inf in x)
     rp = np.array([0, 3, 3, 4], np.int32)

@@ -1,0 +1,143 @@
+"""GPU parity tests for triangular_solve_inspect / triangular_solve (level-scheduled SpTRSV,
+csrc/trsv.cu): BIT-EXACT against the committed output of the real reference on its own
+fixtures (test/gtest/triangular_solve_test.cpp: generate_csr over util::square_dims, values
+scaled by 1e-3), against the oracle on every type combination, triangle, diagonal mode and
+scaling, the level sets against their plain definition, and the error behaviour."""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+import spblas_reference_b200 as sb
+from spblas_reference_b200 import generators as G
+from conftest import GOLDEN
+from helpers import csr_on_device, dev
+
+pytestmark = pytest.mark.gpu
+SQUARE_DIMS = [(1000, 1000, 100), (100, 100, 100), (40, 40, 1000)]
+UPLO = {0: sb.lower_triangle, 1: sb.upper_triangle}
+DIAG = {0: sb.explicit_diagonal, 1: sb.implicit_unit_diagonal}
+
+
+def _solve(a, upper, unit, b, m, info=None, alpha_a=None, alpha_b=None, inplace=False):
+    bd = dev(b)
+    x = bd if inplace else torch.full((m,), float("nan"), dtype=bd.dtype, device="cuda")
+    av = sb.scaled(alpha_a, a) if alpha_a is not None else a
+    bv = sb.scaled(alpha_b, bd) if alpha_b is not None else bd
+    if info is None:
+        sb.triangular_solve(av, UPLO[upper], DIAG[unit], bv, x)
+    else:
+        sb.triangular_solve(info, av, UPLO[upper], DIAG[unit], bv, x)
+    torch.cuda.synchronize()
+    return x.cpu().numpy()
+
+
+@pytest.mark.parametrize("dims", SQUARE_DIMS)
+def test_reference_triangular_solve_fixtures(cuda, oracle, dims):
+    g = np.load(f"{GOLDEN}/trsv_square_dims.npz")
+    m, _, nnz = dims
+    key = f"{m}_{nnz}"
+    b = g[f"b_{key}"]
+    a = csr_on_device(g[f"values_{key}"], g[f"ptr_{key}"], g[f"ind_{key}"], (m, m))
+    ad = csr_on_device(g[f"dvalues_{key}"], g[f"dptr_{key}"], g[f"dind_{key}"], (m, m))
+    for upper, name in ((0, "lower"), (1, "upper")):
+        assert np.array_equal(_solve(a, upper, 1, b, m), g[f"x_unit_{name}_{key}"])
+        assert np.array_equal(_solve(ad, upper, 0, b, m), g[f"x_explicit_{name}_{key}"])
+        assert np.array_equal(_solve(ad, upper, 0, b, m, alpha_b=1.2),
+                              g[f"x_explicit_scaled_{name}_{key}"])
+        # the reference test itself (triangular_solve_test.cpp:70-88): b = 0, x starts at 1
+        info = sb.triangular_solve_inspect(sb.matrix_opt(a), UPLO[upper], DIAG[1],
+                                           dev(np.zeros(m, np.float32)), torch.ones(m, device="cuda"))
+        x = torch.ones(m, device="cuda")
+        sb.triangular_solve(info, sb.matrix_opt(a), UPLO[upper], DIAG[1], dev(np.zeros(m, np.float32)), x)
+        assert not x.cpu().numpy().any()
+        info.close()
+
+
+def _tri_matrix(rng, m, kind, vt, it, ot):
+    if kind == "short":
+        lens = rng.integers(0, 10, size=m)
+    elif kind == "mixed":
+        lens = rng.integers(0, 5, size=m)
+        lens[rng.integers(0, m, size=max(1, m // 40))] = rng.integers(40, 300, size=max(1, m // 40))
+    else:                                          # "chain": every row reads its neighbour
+        lens = np.ones(m, dtype=np.int64)
+    rp = np.concatenate([[0], np.cumsum(lens + 1)]).astype(ot)          # +1: the diagonal
+    ci = np.empty(int(rp[-1]), dtype=it)
+    v = np.empty(int(rp[-1]), dtype=vt)
+    for i in range(m):
+        n_off = int(lens[i])
+        cols = rng.integers(0, m, size=n_off) if kind != "chain" else np.array([max(i - 1, 0)])
+        pos = int(rng.integers(0, n_off + 1))                           # diagonal anywhere in the row
+        row_c = np.insert(cols, pos, i)
+        row_v = np.insert(0.3 * rng.standard_normal(n_off) / max(n_off, 1), pos, 1.5 + rng.random())
+        ci[rp[i]:rp[i + 1]] = row_c
+        v[rp[i]:rp[i + 1]] = row_v
+    return v, rp, ci
+
+
+@pytest.mark.parametrize("kind", ["short", "mixed", "chain"])
+@pytest.mark.parametrize("types", [(np.float32, np.int32, np.int32), (np.float64, np.int32, np.int64),
+                                   (np.float64, np.int32, np.int32), (np.float32, np.int64, np.int64)])
+def test_trsv_bit_exact_vs_oracle(cuda, oracle, kind, types):
+    vt, it, ot = types
+    rng = np.random.default_rng(zlib.crc32(f"trsv{kind}{vt.__name__}{ot.__name__}".encode()))
+    m = 1500 if kind != "chain" else 700
+    v, rp, ci = _tri_matrix(rng, m, kind, vt, it, ot)
+    b = rng.standard_normal(m).astype(vt)
+    a = csr_on_device(v, rp, ci, (m, m))
+    for upper in (0, 1):
+        for unit in (0, 1):
+            info = sb.triangular_solve_inspect(a, UPLO[upper], DIAG[unit], dev(b),
+                                               torch.empty(m, dtype=dev(b).dtype, device="cuda"))
+            levels = oracle.trsv_levels(m, rp, ci, upper=bool(upper))
+            assert info.trsv_levels == int(levels.max()) + 1
+            for kw in ({}, {"alpha_b": 1.2}, {"alpha_a": 0.5, "alpha_b": -2.0}):
+                want = oracle.trsv(m, rp, ci, v, b, upper=upper, unit=unit, **kw)
+                got = _solve(a, upper, unit, b, m, info=info, **kw)
+                assert np.array_equal(got, want, equal_nan=True), (kind, upper, unit, kw)
+            assert info.last_launches == info.trsv_levels
+            # no info (inspect + solve in one call), and b aliased with x
+            assert np.array_equal(_solve(a, upper, unit, b, m), oracle.trsv(m, rp, ci, v, b, upper=upper, unit=unit),
+                                  equal_nan=True)
+            assert np.array_equal(_solve(a, upper, unit, b, m, info=info, inplace=True),
+                                  oracle.trsv(m, rp, ci, v, b, upper=upper, unit=unit), equal_nan=True)
+            # values change, structure does not
+            v2 = v * vt(0.5)
+            a.values.copy_(dev(v2))
+            assert np.array_equal(_solve(a, upper, unit, b, m, info=info),
+                                  oracle.trsv(m, rp, ci, v2, b, upper=upper, unit=unit), equal_nan=True)
+            a.values.copy_(dev(v))
+            info.close()
+
+
+def test_trsv_poisson_levels_and_errors(cuda, oracle):
+    g = 64
+    v, rp, ci, shape = G.poisson2d_csr(g, torch.float64, "cuda:0")
+    a = sb.csr_view(v, rp, ci, shape, int(ci.numel()))
+    m = shape[0]
+    b = np.random.default_rng(3).standard_normal(m)
+    x = torch.empty(m, dtype=torch.float64, device="cuda")
+    info = sb.triangular_solve_inspect(a, sb.lower_triangle, sb.explicit_diagonal, dev(b), x)
+    assert info.trsv_levels == 2 * g - 1                    # anti-diagonals of the grid
+    sb.triangular_solve(info, a, sb.lower_triangle, sb.explicit_diagonal, dev(b), x)
+    want = oracle.trsv(m, rp.cpu().numpy(), ci.cpu().numpy(), v.cpu().numpy(), b)
+    assert np.array_equal(x.cpu().numpy(), want)
+    info.close()
+    # a row without a stored diagonal under explicit_diagonal: refused at inspect
+    rp2 = np.array([0, 1, 2, 3], np.int32)
+    a2 = csr_on_device(np.ones(3, np.float32), rp2, np.array([0, 0, 2], np.int32), (3, 3))
+    bb, xx = torch.ones(3, device="cuda"), torch.empty(3, device="cuda")
+    with pytest.raises(RuntimeError, match="no diagonal"):
+        sb.triangular_solve(a2, sb.lower_triangle, sb.explicit_diagonal, bb, xx)
+    sb.triangular_solve(a2, sb.lower_triangle, sb.implicit_unit_diagonal, bb, xx)   # fine without
+    assert xx.cpu().tolist() == [1.0, 0.0, 1.0]
+    with pytest.raises(ValueError):                          # not square
+        sb.triangular_solve(csr_on_device(np.ones(1, np.float32), np.array([0, 1, 1], np.int32),
+                                          np.array([0], np.int32), (2, 3)),
+                            sb.lower_triangle, sb.implicit_unit_diagonal, torch.ones(2, device="cuda"),
+                            torch.ones(3, device="cuda"))
+    with pytest.raises(ValueError):                          # wrong vector length
+        sb.triangular_solve(a2, sb.lower_triangle, sb.implicit_unit_diagonal,
+                            torch.ones(4, device="cuda"), xx)

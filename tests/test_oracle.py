@@ -279,3 +279,86 @@ def test_transpose_equals_csc_image(oracle):
     tv, trp, tci = oracle.transpose((m, n), rp, ci, v)
     i_rp, i_ci, perm = oracle.csc_row_major_image((n, m), rp, ci)
     assert np.array_equal(trp, i_rp) and np.array_equal(tci, i_ci) and np.array_equal(tv, v[perm])
+
+
+# ---------------------------------------------------------------------------------------
+# triangular_solve: oracle restatement of triangular_solve_impl.hpp:44-94
+# ---------------------------------------------------------------------------------------
+SQUARE_DIMS = [(1000, 1000, 100), (100, 100, 100), (40, 40, 1000)]        # util.hpp:31-33
+
+
+def _reference_test_trsv(m, rowptr, colind, values, b, upper, unit):
+    # reference_triangular_solve of test/gtest/triangular_solve_test.cpp:6-58 (tmp = b - sum)
+    x = np.zeros(m, dtype=values.dtype)
+    for row in (range(m - 1, -1, -1) if upper else range(m)):
+        tmp, diag = values.dtype.type(b[row]), values.dtype.type(0)
+        for j in range(rowptr[row], rowptr[row + 1]):
+            col = colind[j]
+            if (col > row) if upper else (col < row):
+                tmp = values.dtype.type(tmp - values.dtype.type(values[j] * x[col]))
+            elif col == row:
+                diag = values[j]
+        x[row] = tmp if unit else values.dtype.type(tmp / diag)
+    return x
+
+
+@pytest.mark.parametrize("dims", SQUARE_DIMS)
+def test_trsv_matches_golden_and_reference_test(oracle, dims):
+    g = np.load(f"{GOLDEN}/trsv_square_dims.npz")
+    m, _, nnz = dims
+    key = f"{m}_{nnz}"
+    v, rp, ci, b = g[f"values_{key}"], g[f"ptr_{key}"], g[f"ind_{key}"], g[f"b_{key}"]
+    dv, drp, dci = g[f"dvalues_{key}"], g[f"dptr_{key}"], g[f"dind_{key}"]
+    for upper, name in ((0, "lower"), (1, "upper")):
+        x = oracle.trsv(m, rp, ci, v, b, upper=upper, unit=True)
+        assert np.array_equal(x, g[f"x_unit_{name}_{key}"])
+        # the reference test's own solver (b - sum formed the other way round: a different
+        # rounding sequence, amplified along the substitution) agrees to a few 1e-5
+        assert np.allclose(_reference_test_trsv(m, rp, ci, v, b, upper, True), x, rtol=2e-4, atol=1e-5)
+        xe = oracle.trsv(m, drp, dci, dv, b, upper=upper, unit=False)
+        assert np.array_equal(xe, g[f"x_explicit_{name}_{key}"])
+        assert np.allclose(_reference_test_trsv(m, drp, dci, dv, b, upper, False), xe, rtol=2e-4, atol=1e-5)
+        xs = oracle.trsv(m, drp, dci, dv, b, upper=upper, unit=False, alpha_b=1.2)
+        assert np.array_equal(xs, g[f"x_explicit_scaled_{name}_{key}"])
+    # the reference test itself: b = 0 gives x = 0 whatever x held (triangular_solve_test.cpp:70-88)
+    assert not oracle.trsv(m, rp, ci, v, np.zeros(m, np.float32), unit=True, x0=np.ones(m, np.float32)).any()
+
+
+def test_trsv_against_real_reference_when_present(oracle):
+    """Bit-exact against the real spblas::triangular_solve for every type combination, both
+    triangles, both diagonal modes, scaled(a) / scaled(b) — including the reference's use of
+    the previous row's diagonal when a row stores none (random matrices have such rows)."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(41)
+    for (vt, it, ot) in [(np.float32, np.int32, np.int32), (np.float32, np.int32, np.int64),
+                         (np.float64, np.int32, np.int32), (np.float64, np.int32, np.int64),
+                         (np.float32, np.int64, np.int64)]:
+        m = 211
+        lens = rng.integers(0, 14, size=m)
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(ot)
+        ci = rng.integers(0, m, size=int(rp[-1])).astype(it)
+        v = (0.05 * rng.standard_normal(len(ci))).astype(vt)
+        b = rng.standard_normal(m).astype(vt)
+        for upper in (0, 1):
+            for unit in (0, 1):
+                for kw in ({}, {"alpha_b": 1.2}, {"alpha_a": 0.5}, {"alpha_a": -2.0, "alpha_b": 3.0}):
+                    got = oracle.trsv(m, rp, ci, v, b, upper=upper, unit=unit, **kw)
+                    want = oracle.trsv(m, rp, ci, v, b, upper=upper, unit=unit, impl="reference", **kw)
+                    assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_trsv_levels(oracle):
+    # 5-point Poisson on a g x g grid: the lower triangle has 2g - 1 levels (anti-diagonals)
+    import torch
+    from spblas_reference_b200 import generators as G
+    g = 9
+    v, rp, ci, shape = G.poisson2d_csr(g, torch.float64, "cpu")
+    lv = oracle.trsv_levels(shape[0], rp.numpy(), ci.numpy())
+    assert lv.max() + 1 == 2 * g - 1
+    assert np.array_equal(lv, (np.arange(g * g) // g) + (np.arange(g * g) % g))
+    lu = oracle.trsv_levels(shape[0], rp.numpy(), ci.numpy(), upper=True)
+    assert np.array_equal(lu, lv[::-1])
+    # a diagonal matrix has one level; a bidiagonal one has m
+    assert oracle.trsv_levels(4, [0, 1, 2, 3, 4], [0, 1, 2, 3]).max() == 0
+    assert oracle.trsv_levels(4, [0, 1, 3, 5, 7], [0, 0, 1, 1, 2, 2, 3]).tolist() == [0, 1, 2, 3]
