@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2",
-                    choices=["c1", "c2", "c3k32", "c3k128", "c4", "c5", "t1", "t4", "c1t", "c4t"])
+                    choices=["c1", "c2", "c3k32", "c3k128", "c4", "c5", "t1", "t4", "c1t", "c4t", "trsv"])
     ap.add_argument("--scale", type=int, default=0,
                     help="C5 R-MAT scale (default 24 + log2(N): 16.7M rows per GPU)")
     ap.add_argument("--grid", type=int, default=4096, help="C2 grid edge (per GPU)")
@@ -257,6 +257,10 @@ def main():
                barrier, max_over_ranks, sum_over_ranks)
         if world > 1:
             dist.destroy_process_group()
+        return
+    if args.workload == "trsv":
+        from bench_extra import run_trsv        # triangular solve
+        run_trsv(args, sb, G, dev, peak, peak_src, ClockSampler(local_rank))
         return
     if args.workload in ("t1", "t4"):
         from bench_extra import run_transpose   # CSR -> CSR transpose

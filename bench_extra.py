@@ -363,6 +363,72 @@ def run_transpose(args, sb, G, dev, peak, peak_src, sampler):
     print(json.dumps(line), flush=True)
 
 
+def run_trsv(args, sb, G, dev, peak, peak_src, sampler):
+    """--workload trsv: triangular_solve on the lower triangle (explicit diagonal) of the C2
+    matrix — 5-point Poisson on a 4096 x 4096 grid, fp64/int32: 16.7 M unknowns in 8191 level
+    sets (the anti-diagonals of the grid).  A step is one solve; the level launches are
+    replayed from a CUDA graph, with the level-by-level launch time beside it."""
+    import numpy as np
+    K, W = max(1, args.steps), max(3, args.warmup)
+    g = args.grid
+    v, rp, ci, shape = G.poisson2d_csr(g, torch.float64, dev)
+    m, nnz = shape[0], int(ci.numel())
+    a = sb.csr_view(v, rp, ci, shape, nnz)
+    b = G.dense_uniform((m,), 7, torch.float64, dev)
+    x = torch.empty(m, dtype=torch.float64, device=dev)
+    t0 = time.perf_counter()
+    info = sb.triangular_solve_inspect(a, sb.lower_triangle, sb.explicit_diagonal, b, x)
+    torch.cuda.synchronize()
+    inspect_ms = (time.perf_counter() - t0) * 1e3
+    solve = lambda i: sb.triangular_solve(info, a, sb.lower_triangle, sb.explicit_diagonal, b, x)
+    sampler.start()
+    ms = _time_loop(solve, K, W)
+    clocks = sampler.stop()
+    os.environ["SPBLAS_B200_TRSV_GRAPH"] = "0"
+    info0 = sb.triangular_solve_inspect(a, sb.lower_triangle, sb.explicit_diagonal, b, x)
+    os.environ.pop("SPBLAS_B200_TRSV_GRAPH")
+    x0 = torch.empty_like(x)
+    ms_direct = _time_loop(lambda i: sb.triangular_solve(info0, a, sb.lower_triangle,
+                                                         sb.explicit_diagonal, b, x0), max(3, K // 4), 2)
+    same_paths = bool(torch.equal(x, x0))
+    used = (nnz + m) // 2                       # stored entries of the lower triangle incl. diagonal
+    flops = 2.0 * used
+    nbytes = nnz * 12 + (m + 1) * 4 + 3 * m * 8   # whole rows are read; b read, x read and written
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        impl = "reference" if O.have_ref() else "oracle"
+        vh, rph, cih, bh = v.cpu().numpy(), rp.cpu().numpy(), ci.cpu().numpy(), b.cpu().numpy()
+        t0 = time.perf_counter()
+        want = O.trsv(m, rph, cih, vh, bh, upper=False, unit=False, impl=impl)
+        sec = time.perf_counter() - t0
+        cpu = {"value": flops / sec / 1e9, "unit": "GFLOP/s", "cores": 1,
+               "kind": "reference" if impl == "reference" else "port", "seconds": sec,
+               "sample": "the full solve, once (the reference's triangular_solve is serial)",
+               "bit_identical_to_gpu_result": bool(np.array_equal(want, x.cpu().numpy())),
+               "host_cores_available": os.cpu_count()}
+    line = {
+        "metric": "CSR SpTRSV GFLOP/s", "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s",
+        "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"lower-triangular solve (explicit diagonal) with the C2 matrix, "
+                               f"poisson2d {g}x{g}, fp64/int32", "rows": m, "nnz": nnz,
+                   "levels": info.trsv_levels, "inspect_ms": inspect_ms,
+                   "inspect_sweeps": info.trsv_sweeps,
+                   "ms_per_step_level_by_level_launches": ms_direct,
+                   "graph_and_direct_bit_identical": same_paths,
+                   "us_per_level": ms * 1e3 / max(info.trsv_levels, 1)},
+        "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
+                     "note": "latency-bound by construction: 8191 dependent levels of <= 4096 rows; "
+                             "the figure of merit is microseconds per level, not bytes per second"},
+        "clocks": clocks, "gpu_launches": int(info.trsv_levels) * K, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_c5(args, sb, G, dev, peak, peak_src, sampler, world, rank, barrier, max_over_ranks,
            sum_over_ranks):
     """C5: R-MAT (edge factor 16) CSR SpMV fp64 with int32 indices and int64 offsets,

@@ -72,6 +72,11 @@ void release_all(spblas_b200_plan* p) {
     release(*b);
   release(p->hc_colmax);
   release_host_exec(p);
+  release_trsv_graphs(p);
+  release(p->trsv_params);
+  if (p->trsv_capture_stream)
+    cudaStreamDestroy(p->trsv_capture_stream);
+  p->trsv_capture_stream = nullptr;
 }
 
 bool valid_index_type(int t) { return t == SPBLAS_B200_I32 || t == SPBLAS_B200_I64; }
@@ -188,6 +193,8 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
   }
   if (const char* v = std::getenv("SPBLAS_B200_WS_CARVEOUT"))
     p->ws_carveout = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_TRSV_GRAPH"))
+    p->trsv_use_graph = std::atoi(v) != 0;
   if (const char* v = std::getenv("SPBLAS_B200_HOST_CHUNKS"))
     p->host_chunks_override = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_SPMM_VARIANT"))

@@ -119,6 +119,11 @@ struct spblas_b200_plan {
   b200::DeviceBuffer trsv_tmp0, trsv_tmp1;
   b200::DeviceBuffer trsv_level_ptr; // int64 offsets of the levels in trsv_order
   std::vector<int64_t> trsv_level_ptr_h;
+  // the level launches captured as a CUDA graph (one per value width), replayed per solve
+  bool trsv_use_graph = true;            // env SPBLAS_B200_TRSV_GRAPH=0 launches level by level
+  cudaGraphExec_t trsv_graph[2] = {nullptr, nullptr};
+  cudaStream_t trsv_capture_stream = nullptr;
+  b200::DeviceBuffer trsv_params;        // operands of the current solve, read by the graph's kernels
 
   // ---- merge-path partition --------------------------------------------------
   int tile_items = b200::kSpmvTileItems;
@@ -236,6 +241,7 @@ void release_host_exec(spblas_b200_plan* p);
 // trsv.cu
 int trsv_inspect(spblas_b200_plan* p, int64_t m, const void* d_rowptr, const void* d_colind,
                  int upper, int unit);
+void release_trsv_graphs(spblas_b200_plan* p);
 int trsv_solve(spblas_b200_plan* p, int val_type, const void* alpha_a, const void* alpha_b,
                const void* values, const void* b, void* x);
 // spmm.cu

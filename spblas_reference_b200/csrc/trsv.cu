@@ -111,16 +111,22 @@ __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(
 __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
 
+// Operands of a solve as the kernels of a captured graph see them: the graph is built
+// once per plan and value type, the operands of each call are copied here first.
+struct TrsvParams {
+  const void* values;
+  const void* b;
+  void* x;
+  double alpha_a, alpha_b; // (float factors are stored widened; exact)
+  int has_aa, has_ab;
+};
+
 template <typename T, typename I, typename O>
-__global__ void __launch_bounds__(128)
-trsv_level_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
-                  const T* __restrict__ values, const int* __restrict__ rows, int64_t nrows,
-                  int upper, int unit, int has_aa, T alpha_a, int has_ab, T alpha_b,
-                  const T* b, T* x) {
-  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= nrows)
-    return;
-  const int64_t i = rows[t];
+__device__ __forceinline__ void trsv_row(const O* __restrict__ rowptr,
+                                         const I* __restrict__ colind,
+                                         const T* __restrict__ values, int64_t i, int upper,
+                                         int unit, int has_aa, T alpha_a, int has_ab,
+                                         T alpha_b, const T* b, T* x) {
   T dot = T(0), diag = T(0);
   for (O p = rowptr[i]; p < rowptr[i + 1]; ++p) {
     const int64_t k = int64_t(colind[p]);
@@ -138,6 +144,44 @@ trsv_level_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
   const T num = sub_rn(b_i, dot);
   x[i] = unit ? num : div_rn(num, diag);
 }
+
+template <typename T, typename I, typename O>
+__global__ void __launch_bounds__(128)
+trsv_level_graph_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
+                        const int* __restrict__ rows, int64_t nrows, int upper, int unit,
+                        const TrsvParams* __restrict__ prm) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= nrows)
+    return;
+  trsv_row<T, I, O>(rowptr, colind, static_cast<const T*>(prm->values), rows[t], upper, unit,
+                    prm->has_aa, T(prm->alpha_a), prm->has_ab, T(prm->alpha_b),
+                    static_cast<const T*>(prm->b), static_cast<T*>(prm->x));
+}
+
+template <typename T, typename I, typename O>
+__global__ void __launch_bounds__(128)
+trsv_level_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
+                  const T* __restrict__ values, const int* __restrict__ rows, int64_t nrows,
+                  int upper, int unit, int has_aa, T alpha_a, int has_ab, T alpha_b,
+                  const T* b, T* x) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= nrows)
+    return;
+  trsv_row<T, I, O>(rowptr, colind, values, rows[t], upper, unit, has_aa, alpha_a, has_ab,
+                    alpha_b, b, x);
+}
+
+} // namespace
+
+void release_trsv_graphs(spblas_b200_plan* p) {
+  for (int i = 0; i < 2; ++i) {
+    if (p->trsv_graph[i])
+      cudaGraphExecDestroy(p->trsv_graph[i]);
+    p->trsv_graph[i] = nullptr;
+  }
+}
+
+namespace {
 
 int check(spblas_b200_plan* p, const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -168,6 +212,7 @@ int trsv_inspect_typed(spblas_b200_plan* p, int64_t m, const void* d_rowptr,
   int* changed = reinterpret_cast<int*>(stats + 8);
   p->trsv_level_ptr_h.assign(1, 0);
   p->trsv_levels = 0;
+  release_trsv_graphs(p); // they replay the previous structure's levels
   if (m == 0)
     return SPBLAS_B200_SUCCESS;
 
@@ -238,6 +283,55 @@ int trsv_solve_typed(spblas_b200_plan* p, const void* alpha_a, const void* alpha
   const T ab = alpha_b ? *static_cast<const T*>(alpha_b) : T(1);
   const int* order = static_cast<const int*>(p->trsv_order.p);
   int launches = 0;
+  // Deep level structures (a 4096 x 4096 stencil has 8191 levels) are bound by launch
+  // overhead: the level launches are captured ONCE into a CUDA graph whose kernels read
+  // the operands of the call from a small parameter block, and every solve replays it.
+  const int slot = sizeof(T) == 8 ? 1 : 0;
+  if (p->trsv_use_graph && p->trsv_levels >= 16) {
+    if (int rc = reserve(p, p->trsv_params, sizeof(TrsvParams)))
+      return rc;
+    TrsvParams h;
+    h.values = values;
+    h.b = b;
+    h.x = x;
+    h.alpha_a = double(aa);
+    h.alpha_b = double(ab);
+    h.has_aa = alpha_a != nullptr;
+    h.has_ab = alpha_b != nullptr;
+    B200_CUDA_TRY(p, cudaMemcpyAsync(p->trsv_params.p, &h, sizeof(h), cudaMemcpyHostToDevice,
+                                     p->stream));
+    if (!p->trsv_graph[slot]) {
+      // capture on a private stream: the plan's stream may be the legacy default stream,
+      // which cannot be captured
+      if (!p->trsv_capture_stream)
+        B200_CUDA_TRY(p, cudaStreamCreateWithFlags(&p->trsv_capture_stream, cudaStreamNonBlocking));
+      cudaStream_t cs = p->trsv_capture_stream;
+      B200_CUDA_TRY(p, cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+      for (int64_t l = 0; l < p->trsv_levels; ++l) {
+        const int64_t r0 = p->trsv_level_ptr_h[size_t(l)], r1 = p->trsv_level_ptr_h[size_t(l) + 1];
+        if (r1 <= r0)
+          continue;
+        trsv_level_graph_kernel<T, I, O><<<unsigned((r1 - r0 + 127) / 128), 128, 0, cs>>>(
+            static_cast<const O*>(p->trsv_rowptr), static_cast<const I*>(p->trsv_colind),
+            order + r0, r1 - r0, p->trsv_upper, p->trsv_unit,
+            static_cast<const TrsvParams*>(p->trsv_params.p));
+      }
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamEndCapture(cs, &graph);
+      if (e != cudaSuccess)
+        return cuda_fail(p, e, "cudaStreamEndCapture(trsv levels)");
+      e = cudaGraphInstantiate(&p->trsv_graph[slot], graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) {
+        p->trsv_graph[slot] = nullptr;
+        return cuda_fail(p, e, "cudaGraphInstantiate(trsv levels)");
+      }
+    }
+    B200_CUDA_TRY(p, cudaGraphLaunch(p->trsv_graph[slot], p->stream));
+    p->last_launches = p->trsv_levels;
+    p->total_launches += p->trsv_levels;
+    return SPBLAS_B200_SUCCESS;
+  }
   for (int64_t l = 0; l < p->trsv_levels; ++l) {
     const int64_t r0 = p->trsv_level_ptr_h[size_t(l)], r1 = p->trsv_level_ptr_h[size_t(l) + 1];
     if (r1 <= r0)

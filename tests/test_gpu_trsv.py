@@ -77,10 +77,14 @@ def _tri_matrix(rng, m, kind, vt, it, ot):
     return v, rp, ci
 
 
+@pytest.mark.parametrize("graph", ["1", "0"])
 @pytest.mark.parametrize("kind", ["short", "mixed", "chain"])
 @pytest.mark.parametrize("types", [(np.float32, np.int32, np.int32), (np.float64, np.int32, np.int64),
                                    (np.float64, np.int32, np.int32), (np.float32, np.int64, np.int64)])
-def test_trsv_bit_exact_vs_oracle(cuda, oracle, kind, types):
+def test_trsv_bit_exact_vs_oracle(cuda, oracle, monkeypatch, kind, types, graph):
+    # graph = 1: the level launches replayed from a CUDA graph (plans with >= 16 levels);
+    # graph = 0: launched level by level
+    monkeypatch.setenv("SPBLAS_B200_TRSV_GRAPH", graph)
     vt, it, ot = types
     rng = np.random.default_rng(zlib.crc32(f"trsv{kind}{vt.__name__}{ot.__name__}".encode()))
     m = 1500 if kind != "chain" else 700
