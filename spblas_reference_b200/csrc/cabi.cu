@@ -193,6 +193,8 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
   }
   if (const char* v = std::getenv("SPBLAS_B200_WS_CARVEOUT"))
     p->ws_carveout = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_TRSV_INSPECT"))
+    p->trsv_relax_inspect = std::string(v) == "relax";
   if (const char* v = std::getenv("SPBLAS_B200_TRSV_GRAPH"))
     p->trsv_use_graph = std::atoi(v) != 0;
   if (const char* v = std::getenv("SPBLAS_B200_HOST_CHUNKS"))
@@ -387,6 +389,7 @@ int spblas_b200_trsv_inspect(spblas_b200_plan* p, int64_t m, int64_t nnz,
   p->trsv_upper = upper ? 1 : 0;
   p->trsv_unit = unit_diagonal ? 1 : 0;
   p->trsv_m = m;
+  p->trsv_nnz = nnz;
   p->trsv_rowptr = d_rowptr;
   p->trsv_colind = d_colind;
   // the plan now describes a triangular solve, not a product

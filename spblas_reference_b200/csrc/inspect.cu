@@ -644,6 +644,27 @@ int run_transpose(spblas_b200_plan* p, int val_type, const void* values, void* t
              : transpose_typed<int32_t>(p, type_size_val(val_type), values, t_values);
 }
 
+// The column structure of a square CSR matrix — rowptr/colind of its transpose — in the
+// plan's own_* buffers (the CSC-image builder run on A's arrays read column-major).
+// Used by the triangular solve's level analysis: column k lists the rows that read x_k.
+int build_column_structure(spblas_b200_plan* p, int64_t m, int64_t nnz, const void* d_rowptr,
+                           const void* d_colind) {
+  p->format = SPBLAS_B200_CSC;
+  p->m = m;
+  p->n = m;
+  p->nnz = nnz;
+  p->user_ptr = d_rowptr;
+  p->user_ind = d_colind;
+  const bool i64 = p->idx_type == SPBLAS_B200_I64, o64 = p->off_type == SPBLAS_B200_I64;
+  if (!i64 && !o64)
+    return build_row_major_image<int32_t, int32_t>(p);
+  if (!i64 && o64)
+    return build_row_major_image<int32_t, int64_t>(p);
+  if (i64 && !o64)
+    return build_row_major_image<int64_t, int32_t>(p);
+  return build_row_major_image<int64_t, int64_t>(p);
+}
+
 // out[q] = values[perm[q]] for the whole image (the value half of run_transpose)
 int gather_permuted_values(spblas_b200_plan* p, int val_type, const void* values, void* out) {
   return p->off_type == SPBLAS_B200_I64

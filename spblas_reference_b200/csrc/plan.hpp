@@ -111,7 +111,7 @@ struct spblas_b200_plan {
   // ---- triangular solve (trsv.cu): level sets of the inspected triangle ---------------
   bool trsv_ready = false;
   int trsv_upper = 0, trsv_unit = 0;
-  int64_t trsv_m = 0, trsv_levels = 0, trsv_sweeps = 0;
+  int64_t trsv_m = 0, trsv_nnz = 0, trsv_levels = 0, trsv_sweeps = 0;
   const void* trsv_rowptr = nullptr;
   const void* trsv_colind = nullptr;
   b200::DeviceBuffer trsv_level;     // int32 per row
@@ -121,6 +121,7 @@ struct spblas_b200_plan {
   std::vector<int64_t> trsv_level_ptr_h;
   // the level launches captured as a CUDA graph (one per value width), replayed per solve
   bool trsv_use_graph = true;            // env SPBLAS_B200_TRSV_GRAPH=0 launches level by level
+  bool trsv_relax_inspect = false;       // env SPBLAS_B200_TRSV_INSPECT=relax: relaxation sweeps instead of frontiers
   cudaGraphExec_t trsv_graph[2] = {nullptr, nullptr};
   cudaStream_t trsv_capture_stream = nullptr;
   b200::DeviceBuffer trsv_params;        // operands of the current solve, read by the graph's kernels
@@ -222,6 +223,8 @@ int build_stream_partition(spblas_b200_plan* p, int64_t streams);
 int build_ws_partition(spblas_b200_plan* p, int64_t resident_warps);
 int run_transpose(spblas_b200_plan* p, int val_type, const void* values, void* t_rowptr,
                   void* t_colind, void* t_values);
+int build_column_structure(spblas_b200_plan* p, int64_t m, int64_t nnz, const void* d_rowptr,
+                           const void* d_colind);
 int gather_permuted_values(spblas_b200_plan* p, int val_type, const void* values, void* out);
 // spmv.cu
 int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,

@@ -82,6 +82,55 @@ trsv_check_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind, in
   }
 }
 
+// ---- level sets by frontiers (Kahn): O(nnz) in total, one small launch per level --------
+// indeg[i] = stored entries of row i on the dependency side of the diagonal; rows with
+// none are level 0 and are appended to `order`.
+template <typename I, typename O>
+__global__ void __launch_bounds__(256)
+trsv_indegree_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind, int64_t m,
+                     int upper, int* __restrict__ indeg, int* __restrict__ level,
+                     int* __restrict__ order, unsigned long long* __restrict__ count) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < m; i += stride) {
+    int d = 0;
+    for (O p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+      const int64_t k = int64_t(colind[p]);
+      d += (upper ? k > i : k < i) ? 1 : 0;
+    }
+    indeg[i] = d;
+    if (d == 0) {
+      level[i] = 0;
+      order[atomicAdd(count, 1ull)] = int(i);
+    }
+  }
+}
+
+// One level: every row k of the frontier order[f0, f1) is solved now, so every row i that
+// reads x_k (column k of A: t_rowptr / t_colind, the transpose structure) has one
+// dependency less; a row whose count reaches zero joins the next frontier, appended to
+// `order` right behind this one and gets its level.  (The frontier list is in whatever
+// order the atomics produce; the rows are sorted by (level, row) afterwards so that a
+// level's threads walk the matrix in ascending row order.)
+template <typename I, typename O>
+__global__ void __launch_bounds__(256)
+trsv_frontier_kernel(const O* __restrict__ t_rowptr, const I* __restrict__ t_colind,
+                     int64_t f0, int64_t f1, int upper, int next_level,
+                     int* __restrict__ indeg, int* __restrict__ level, int* __restrict__ order,
+                     unsigned long long* __restrict__ count) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t t = f0 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < f1; t += stride) {
+    const int64_t k = order[t];
+    for (O p = t_rowptr[k]; p < t_rowptr[k + 1]; ++p) {
+      const int64_t i = int64_t(t_colind[p]);
+      if (upper ? i < k : i > k)
+        if (atomicSub(&indeg[i], 1) == 1) {
+          level[i] = next_level;
+          order[atomicAdd(count, 1ull)] = int(i);
+        }
+    }
+  }
+}
+
 // out[l] = first position in the sorted level array whose level is >= l
 __global__ void __launch_bounds__(256)
 trsv_level_ptr_kernel(const int* __restrict__ sorted_level, int64_t m, int64_t nlevels,
@@ -232,6 +281,43 @@ int trsv_inspect_typed(spblas_b200_plan* p, int64_t m, const void* d_rowptr,
     return fail(p, SPBLAS_B200_INVALID_STRUCTURE,
                 "explicit_diagonal: " + std::to_string(h_stats[1]) +
                     " row(s) store no diagonal entry");
+  if (!p->trsv_relax_inspect) {
+    // Frontier (Kahn) analysis over the column structure: total work O(nnz), one launch
+    // and one 8-byte read-back per level.
+    if (int rc = build_column_structure(p, m, p->trsv_nnz, d_rowptr, d_colind))
+      return rc;
+    const O* t_rowptr = static_cast<const O*>(p->csr_rowptr);
+    const I* t_colind = static_cast<const I*>(p->csr_colind);
+    int* indeg = sorted_level; // (free until the sort below writes its keys there)
+    unsigned long long* count = stats + 4;
+    trsv_indegree_kernel<I, O><<<grid, 256, 0, s>>>(rowptr, colind, m, upper, indeg, level,
+                                                    order, count);
+    if (int rc = check(p, "trsv_indegree_kernel"))
+      return rc;
+    std::vector<int64_t>& lp = p->trsv_level_ptr_h;
+    lp.assign(1, 0);
+    unsigned long long done = 0;
+    for (;;) {
+      B200_CUDA_TRY(p, cudaMemcpyAsync(&done, count, sizeof(done), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+      const int64_t f0 = lp.back(), f1 = int64_t(done);
+      if (f1 == f0)
+        break; // no new rows: all levels found (or a dependency cycle, checked below)
+      lp.push_back(f1);
+      if (f1 == m)
+        break;
+      const int fgrid = int(std::min<int64_t>((f1 - f0 + 255) / 256, int64_t(p->num_sms) * 16));
+      trsv_frontier_kernel<I, O><<<fgrid, 256, 0, s>>>(t_rowptr, t_colind, f0, f1, upper,
+                                                       int(lp.size()) - 1, indeg, level, order,
+                                                       count);
+      if (int rc = check(p, "trsv_frontier_kernel"))
+        return rc;
+    }
+    if (lp.back() != m)
+      return fail(p, SPBLAS_B200_INVALID_STRUCTURE, "level analysis did not reach every row");
+    p->trsv_sweeps = int64_t(lp.size()) - 1;
+    h_stats[0] = (unsigned long long)(lp.size() - 2); // highest level
+  } else {
   // relaxation sweeps: a level can only grow, and it is final once a sweep changes nothing
   for (int64_t sweep = 0;; ++sweep) {
     if (sweep > m)
@@ -250,6 +336,8 @@ int trsv_inspect_typed(spblas_b200_plan* p, int64_t m, const void* d_rowptr,
   }
   B200_CUDA_TRY(p, cudaMemcpyAsync(h_stats, stats, sizeof(h_stats[0]), cudaMemcpyDeviceToHost, s));
   B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+  }
+  // rows by (level, row): stable sort of the levels carrying the row ids
   const int64_t nlevels = int64_t(h_stats[0]) + 1;
   int end_bit = 1;
   while (end_bit < 31 && (int64_t(1) << end_bit) < nlevels)

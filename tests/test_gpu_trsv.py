@@ -145,3 +145,25 @@ def test_trsv_poisson_levels_and_errors(cuda, oracle):
     with pytest.raises(ValueError):                          # wrong vector length
         sb.triangular_solve(a2, sb.lower_triangle, sb.implicit_unit_diagonal,
                             torch.ones(4, device="cuda"), xx)
+
+
+@pytest.mark.parametrize("inspect", ["frontier", "relax"])
+def test_trsv_level_analysis_variants(cuda, oracle, monkeypatch, inspect):
+    """The frontier (Kahn, default) and the relaxation-sweep level analyses find the same
+    level count and give the same bit-exact solution; duplicate dependency entries and
+    rows with no entries at all included."""
+    monkeypatch.setenv("SPBLAS_B200_TRSV_INSPECT", inspect)
+    rng = np.random.default_rng(77)
+    m = 2000
+    v, rp, ci = _tri_matrix(rng, m, "mixed", np.float64, np.int32, np.int32)
+    # duplicate some dependency entries; the matrix keeps its diagonals
+    ci[rp[500] + 1:rp[501]] = ci[rp[500] + 1] if rp[501] - rp[500] > 1 else ci[rp[500]]
+    b = rng.standard_normal(m)
+    a = csr_on_device(v, rp, ci, (m, m))
+    for upper in (0, 1):
+        info = sb.triangular_solve_inspect(a, UPLO[upper], DIAG[0], dev(b),
+                                           torch.empty(m, dtype=torch.float64, device="cuda"))
+        assert info.trsv_levels == int(oracle.trsv_levels(m, rp, ci, upper=bool(upper)).max()) + 1
+        assert np.array_equal(_solve(a, upper, 0, b, m, info=info),
+                              oracle.trsv(m, rp, ci, v, b, upper=upper, unit=False), equal_nan=True)
+        info.close()
