@@ -1,6 +1,6 @@
 #!/bin/bash
-# last pass of the round: memcheck/racecheck of the kernels added this round, the transpose
-# workloads, then parity + smoke + headline bench exactly as the driver runs them
+# memcheck / racecheck over the SpMV variants, the host-buffer execute and the transpose, then the
+# transpose workloads, parity + smoke + headline bench exactly as the driver runs them
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 SEL="every_kernel_variant and mixed or host_execute_bit_identical and hub and 16 or transpose_vs_oracle and hub or reference_transpose_test"
