@@ -48,3 +48,59 @@ def test_bad_call_shapes():
         sb.multiply(_csr())
     with pytest.raises(TypeError):
         sb.multiply_execute(None, _csr(), torch.zeros(4), torch.zeros(3))
+
+
+def test_matrix_opt_detection():
+    a = _csr()
+    assert not views.has_matrix_opt(a) and not views.has_matrix_opt(sb.scaled(2, a))
+    assert views.has_matrix_opt(sb.matrix_opt(a))
+    assert views.has_matrix_opt(sb.scaled(2, sb.matrix_opt(sb.transposed(a))))
+
+
+def test_transpose_argument_checks_follow_the_reference():
+    # algorithms/transpose_impl.hpp:17-25: dimensions first, then the size of b's arrays
+    a = _csr(3, 4)
+    mk = lambda shape, cap: sb.csr_view(torch.zeros(cap), torch.zeros(shape[0] + 1, dtype=torch.int32),
+                                        torch.zeros(cap, dtype=torch.int32), shape, 0)
+    with pytest.raises(ValueError, match="transpose: matrix dimensions are incompatible."):
+        sb.transpose(a, mk((3, 4), 4))
+    with pytest.raises(RuntimeError, match="transpose: Transpose ran out of memory."):
+        sb.transpose(a, mk((4, 3), 3))
+    with pytest.raises(RuntimeError, match="device memory"):      # only then the backend's own rule
+        sb.transpose(a, mk((4, 3), 4))
+    with pytest.raises(TypeError):
+        sb.transpose(a)
+    with pytest.raises(TypeError):
+        sb.transpose_inspect(sb.transposed(a), mk((4, 3), 4))      # csc_view: no overload either
+
+
+def test_triangular_solve_argument_checks():
+    sq = sb.csr_view(torch.zeros(3), torch.tensor([0, 1, 2, 3], dtype=torch.int32),
+                     torch.tensor([0, 1, 2], dtype=torch.int32), (3, 3), 3)
+    b, x = torch.zeros(3), torch.zeros(3)
+    with pytest.raises(TypeError, match="uplo"):
+        sb.triangular_solve(sq, "lower", sb.explicit_diagonal, b, x)
+    with pytest.raises(TypeError, match="diag"):
+        sb.triangular_solve(sq, sb.lower_triangle, None, b, x)
+    with pytest.raises(ValueError, match="square"):
+        sb.triangular_solve(_csr(3, 4), sb.lower_triangle, sb.explicit_diagonal, b, torch.zeros(4))
+    with pytest.raises(ValueError, match="dimensions are incompatible"):
+        sb.triangular_solve(sq, sb.upper_triangle, sb.implicit_unit_diagonal, torch.zeros(4), x)
+    with pytest.raises(RuntimeError, match="conjugated"):
+        sb.triangular_solve(sb.conjugated(sq), sb.lower_triangle, sb.explicit_diagonal, b, x)
+    with pytest.raises(RuntimeError, match="device memory"):
+        sb.triangular_solve(sq, sb.lower_triangle, sb.explicit_diagonal, sb.scaled(2.0, b), x)
+    with pytest.raises(TypeError):
+        sb.triangular_solve(sq, sb.lower_triangle, sb.explicit_diagonal, b)
+    from spblas_reference_b200.triangular_solve import _own_scaling
+    assert _own_scaling(sb.scaled(2.0, sb.matrix_opt(sb.scaled(3.0, sq)))) == 6.0
+    assert _own_scaling(sq) is None
+
+
+def test_host_execute_argument_checks():
+    a = _csr()
+    info = sb.operation_info_t()
+    with pytest.raises(TypeError):
+        sb.multiply_execute_host(None, a, torch.zeros(4), torch.zeros(3))
+    with pytest.raises(RuntimeError, match="device memory"):      # A itself must be on the device
+        sb.multiply_execute_host(info, a, torch.zeros(4), torch.zeros(3))
