@@ -102,7 +102,11 @@ enum {
   SPBLAS_B200_Q_BARRIER_EPOCH = 16, /* int64[1]: fused-exchange steps signalled so far         */
   SPBLAS_B200_Q_BARRIER_TIMEOUT = 17, /* int64[1]: 1 if a fused barrier gave up waiting for a peer */
   SPBLAS_B200_Q_TRSV_LEVELS = 18,   /* int64[1]: level sets of the inspected triangular solve      */
-  SPBLAS_B200_Q_TRSV_SWEEPS = 19    /* int64[1]: relaxation sweeps the level analysis took          */
+  SPBLAS_B200_Q_TRSV_SWEEPS = 19,   /* int64[1]: relaxation sweeps the level analysis took          */
+  SPBLAS_B200_Q_HUB_COUNT = 20,     /* int64[1]: hub columns held in shared memory (0: none / not built) */
+  SPBLAS_B200_Q_HUB_REFS = 21,      /* int64[1]: stored entries that reference a hub column         */
+  SPBLAS_B200_Q_HUB_COLS = 22,      /* int32[hub_count]: the hub columns, ascending                 */
+  SPBLAS_B200_Q_HUB_COLIND = 23     /* int32[nnz]: the plan's re-encoded colind (hub number s -> ~s) */
 };
 
 /* most destinations / peers of a fused exchange (one NVSwitch domain: 8 GPUs) */
@@ -161,6 +165,23 @@ SPBLAS_B200_API int spblas_b200_inspect(spblas_b200_plan* plan, int format,
    drops it; a no-op for CSR plans. */
 SPBLAS_B200_API int spblas_b200_plan_cache_values(spblas_b200_plan* plan, int val_type,
                                                   const void* d_values);
+
+/* Optional: shared-memory residency for the most referenced ("hub") columns of x.
+   For matrices whose columns are very unevenly popular (power-law graphs) the product
+   is bound by the gathers of x that miss L1, not by HBM.  With enable != 0, a plan that
+   would run the general (warp-stream) SpMV kernel counts the references per column on
+   its first product, keeps the columns referenced at least min_count times (0 = twice
+   the SM count), takes the max_cols most referenced of them (0 = what the SM's shared
+   memory holds beside the kernel's own buffers: 49152 4-byte or 20480 8-byte values)
+   and stores a re-encoded copy of colind (nnz * 4 bytes, owned by the plan); the hub
+   kernel then reads x at those columns from shared memory.  Used only if at least 15 %
+   of the stored entries reference a hub; results are bit-identical to the plain kernel's.
+   int32 column indices only; plans inspected through multiply_inspect only (the no-info
+   overloads never analyse).  Also read from the environment at plan creation:
+   SPBLAS_B200_HUB, SPBLAS_B200_HUB_COLS, SPBLAS_B200_HUB_MIN_COUNT.  No reference
+   counterpart (closest: oneMKL's optimize_gemv hint, vendor/onemkl_sycl/spmv_impl.hpp:46-58). */
+SPBLAS_B200_API int spblas_b200_plan_set_hub(spblas_b200_plan* plan, int enable,
+                                             int64_t max_cols, int64_t min_count);
 
 /* ---- execute ------------------------------------------------------------ */
 

@@ -195,6 +195,26 @@ def row_segments(rowptr, seg):
     return out[: 3 * n].reshape(-1, 3)
 
 
+def hub_columns(colind, n_cols, max_cols, min_count):
+    """Definition of the hub-column analysis (csrc/hub.cu; no reference counterpart — the
+    reference gathers x[j] per stored entry, multiply_impl.hpp:48-52): count the references
+    per column, keep the columns referenced >= min_count times, order them by (count
+    descending, column ascending), take the first max_cols, renumber them in ascending
+    column order; a reference to hub number s is re-encoded as ~s.
+    Returns (hub columns ascending, references to them, encoded colind)."""
+    ci = np.asarray(colind).astype(np.int64)
+    counts = np.bincount(ci, minlength=n_cols) if len(ci) else np.zeros(n_cols, np.int64)
+    cand = np.nonzero(counts >= max(int(min_count), 1))[0]
+    order = np.lexsort((cand, -counts[cand]))           # primary: count desc, then column asc
+    top = cand[order][: int(max_cols)]
+    refs = int(counts[top].sum())
+    hubs = np.sort(top)
+    slot = np.full(n_cols, -1, dtype=np.int64)
+    slot[hubs] = np.arange(len(hubs))
+    enc = np.where(slot[ci] >= 0, ~slot[ci], ci).astype(np.int32) if len(ci) else ci.astype(np.int32)
+    return hubs.astype(np.int32), refs, enc
+
+
 def csc_row_major_image(shape, colptr, rowind):
     m, n = shape
     cp, ri = _c(colptr, np.int64), _c(rowind, np.int64)

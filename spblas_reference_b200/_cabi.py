@@ -23,7 +23,8 @@ INSPECT_DEFAULT, INSPECT_LIGHT = 0, 1
 (Q_NUM_TILES, Q_TILE_ITEMS, Q_TILE_STARTS, Q_ROWLEN_HIST, Q_MAX_ROW_LEN, Q_EMPTY_ROWS,
  Q_SPMV_VARIANT, Q_LAST_LAUNCHES, Q_TOTAL_LAUNCHES, Q_CSR_ROWPTR, Q_CSR_COLIND,
  Q_CSR_PERM, Q_NUM_SEGMENTS, Q_SEGMENTS, Q_SPMM_VARIANT, Q_TILE_UNIFORM,
- Q_BARRIER_EPOCH, Q_BARRIER_TIMEOUT, Q_TRSV_LEVELS, Q_TRSV_SWEEPS) = range(20)
+ Q_BARRIER_EPOCH, Q_BARRIER_TIMEOUT, Q_TRSV_LEVELS, Q_TRSV_SWEEPS,
+ Q_HUB_COUNT, Q_HUB_REFS, Q_HUB_COLS, Q_HUB_COLIND) = range(24)
 MAX_PEERS = 8
 HIST_BINS = 40
 
@@ -39,6 +40,7 @@ SYMBOLS = (
     "spblas_b200_spmv_host", "spblas_b200_probe_gather",
     "spblas_b200_transpose_inspect", "spblas_b200_transpose",
     "spblas_b200_plan_cache_values", "spblas_b200_trsv_inspect", "spblas_b200_trsv",
+    "spblas_b200_plan_set_hub",
 )
 
 
@@ -75,6 +77,8 @@ def lib() -> C.CDLL:
     L.spblas_b200_plan_set_stream.restype = i32
     L.spblas_b200_plan_force_variant.argtypes = [vp, i32]
     L.spblas_b200_plan_force_variant.restype = i32
+    L.spblas_b200_plan_set_hub.argtypes = [vp, i32, i64, i64]
+    L.spblas_b200_plan_set_hub.restype = i32
     L.spblas_b200_plan_set_scatter.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64),
                                                C.POINTER(i64), i32]
     L.spblas_b200_plan_set_scatter.restype = i32

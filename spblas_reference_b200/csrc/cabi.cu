@@ -1,6 +1,7 @@
 // cabi.cu — the extern "C" surface declared in include/spblas_b200.h.
 // Argument validation, plan lifetime, error strings and metadata queries.  No
 // compute here; kernels live in inspect.cu / spmv.cu / spmm.cu.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -67,7 +68,7 @@ void release_all(spblas_b200_plan* p) {
                           &p->spmm_carry_row, &p->spmm_carry_val, &p->barrier_state,
                           &p->ws_starts, &p->ws_carry_row, &p->ws_carry_val, &p->own_values,
                           &p->trsv_level, &p->trsv_order, &p->trsv_tmp0, &p->trsv_tmp1,
-                          &p->trsv_level_ptr};
+                          &p->trsv_level_ptr, &p->hub_cols, &p->hub_colind};
   for (DeviceBuffer* b : bufs)
     release(*b);
   release(p->hc_colmax);
@@ -193,6 +194,12 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
   }
   if (const char* v = std::getenv("SPBLAS_B200_WS_CARVEOUT"))
     p->ws_carveout = std::atoi(v);
+  if (const char* v = std::getenv("SPBLAS_B200_HUB"))
+    p->hub_enable = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SPBLAS_B200_HUB_COLS"))
+    p->hub_cap_override = std::max<long long>(0, std::atoll(v));
+  if (const char* v = std::getenv("SPBLAS_B200_HUB_MIN_COUNT"))
+    p->hub_min_count = std::max<long long>(0, std::atoll(v));
   if (const char* v = std::getenv("SPBLAS_B200_TRSV_INSPECT"))
     p->trsv_relax_inspect = std::string(v) == "relax";
   if (const char* v = std::getenv("SPBLAS_B200_TRSV_GRAPH"))
@@ -282,6 +289,21 @@ int spblas_b200_plan_force_variant(spblas_b200_plan* p, int v) {
   return SPBLAS_B200_SUCCESS;
 }
 
+int spblas_b200_plan_set_hub(spblas_b200_plan* p, int enable, int64_t max_cols,
+                             int64_t min_count) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  if (max_cols < 0 || min_count < 0)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "negative hub parameter");
+  p->hub_enable = enable ? 1 : 0;
+  if (p->hub_cap_override != max_cols || p->hub_min_count != min_count)
+    p->hub_state = 0; // the table (if any) was built under other limits
+  p->hub_cap_override = max_cols;
+  p->hub_min_count = min_count;
+  return SPBLAS_B200_SUCCESS;
+}
+
 int spblas_b200_inspect(spblas_b200_plan* p, int format, int64_t m, int64_t n,
                         int64_t nnz, const void* d_ptr, const void* d_ind,
                         int off_type, int idx_type, int64_t k_hint, int flags) {
@@ -291,6 +313,8 @@ int spblas_b200_inspect(spblas_b200_plan* p, int format, int64_t m, int64_t n,
   p->inspected = false;
   p->host_chunks = 0; // the chunk table belongs to the previous structure
   p->cached_values = false;
+  p->hub_state = 0; // so does the hub table
+  p->light_inspect = (flags & SPBLAS_B200_INSPECT_LIGHT) != 0;
   if (format != SPBLAS_B200_CSR && format != SPBLAS_B200_CSC)
     return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "format must be CSR or CSC");
   if (!valid_index_type(off_type) || !valid_index_type(idx_type))
@@ -647,6 +671,19 @@ int spblas_b200_plan_query(spblas_b200_plan* p, int what, void* out,
     return scalar(p->num_segments);
   case SPBLAS_B200_Q_SEGMENTS:
     return device_array(p->segments.p, size_t(p->num_segments) * 3 * sizeof(int64_t));
+  case SPBLAS_B200_Q_HUB_COUNT:
+    return scalar(p->hub_state == 1 ? p->hub_count : 0);
+  case SPBLAS_B200_Q_HUB_REFS:
+    return scalar(p->hub_state == 1 ? p->hub_refs : 0);
+  case SPBLAS_B200_Q_HUB_COLS:
+    return device_array(p->hub_cols.p,
+                        p->hub_state == 1 ? size_t(p->hub_count) * sizeof(int32_t) : 0);
+  case SPBLAS_B200_Q_HUB_COLIND:
+    if (p->hub_state != 1)
+      return device_array(nullptr, 0);
+    return device_array(static_cast<const char*>(p->hub_colind.p) +
+                            size_t(p->base & 3) * sizeof(int32_t),
+                        size_t(p->nnz) * sizeof(int32_t));
   default:
     return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "unknown query selector");
   }

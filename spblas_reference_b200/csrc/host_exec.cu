@@ -144,6 +144,13 @@ int run_spmv_host(spblas_b200_plan* p, int val_type, const void* alpha,
   int variant = 0;
   const int64_t* starts = nullptr;
   int64_t units = 0;
+  // (the hub variant reloads its shared-memory table of x on every launch, and a chunk's
+  // launch would read parts of x that have not arrived yet: chunks take the plain walk)
+  struct Active {
+    spblas_b200_plan* p;
+    explicit Active(spblas_b200_plan* q) : p(q) { p->host_exec_active = true; }
+    ~Active() { p->host_exec_active = false; }
+  } active(p);
   if (int rc = prepare_spmv(p, val_type, values, &variant, &starts, &units))
     return rc;
   if (p->host_chunks == 0 || p->hc_variant != variant) {

@@ -43,6 +43,10 @@ enum SpmvVariant : int {
   // rows reduced out of a per-warp slab with __syncwarp() only: the general path for
   // matrices bound by random gathers of x (needs 16-byte aligned colind/values).
   kVariantWarpStream = 2,
+  // the warp-stream walk with x at the most referenced ("hub") columns held in shared
+  // memory: one CTA of 32 warps per SM, a plan-owned re-encoded copy of colind (hub.cu).
+  // For matrices with skewed column popularity (R-MAT); int32 indices only.
+  kVariantHubStream = 3,
 };
 
 struct DeviceBuffer {
@@ -166,6 +170,22 @@ struct spblas_b200_plan {
   b200::DeviceBuffer ws_carry_row; // int64 per stream
   b200::DeviceBuffer ws_carry_val; // 8 bytes per stream
 
+  // ---- hub columns (spmv_hub_stream_kernel, hub.cu) ----------------------------------
+  // The `hub_count` most referenced columns, ascending, and a copy of the effective
+  // colind in which a reference to hub number s reads ~s.  Built on the first execute
+  // that wants the hub variant (the table's size depends on the value width).
+  int hub_state = 0;           // 0: not analysed for the current structure, 1: table built, -1: analysed, no hubs
+  int hub_enable = 0;          // env SPBLAS_B200_HUB / spblas_b200_plan_set_hub: the automatic choice may pick the hub variant
+  int64_t hub_cap = 0;         // capacity (columns) the table was built for
+  int64_t hub_cap_override = 0; // env SPBLAS_B200_HUB_COLS / set_hub (0: what shared memory holds)
+  int64_t hub_min_count = 0;   // env SPBLAS_B200_HUB_MIN_COUNT / set_hub (0: 2 x SM count)
+  int64_t hub_count = 0;       // H
+  int64_t hub_refs = 0;        // nonzeros that reference a hub column
+  bool light_inspect = false;  // the current structure came from a LIGHT inspect (no-info overloads)
+  bool host_exec_active = false; // inside spblas_b200_spmv_host (chunked launches: no hub variant)
+  b200::DeviceBuffer hub_cols;   // int32[H]
+  b200::DeviceBuffer hub_colind; // int32[(base & 3) + nnz]
+
   // ---- statistics -------------------------------------------------------------
   bool have_hist = false;
   int64_t hist[SPBLAS_B200_HIST_BINS] = {0};
@@ -226,6 +246,9 @@ int run_transpose(spblas_b200_plan* p, int val_type, const void* values, void* t
 int build_column_structure(spblas_b200_plan* p, int64_t m, int64_t nnz, const void* d_rowptr,
                            const void* d_colind);
 int gather_permuted_values(spblas_b200_plan* p, int val_type, const void* values, void* out);
+// hub.cu
+int64_t hub_capacity(const spblas_b200_plan* p, size_t val_bytes, int walk_warps);
+int build_hub_table(spblas_b200_plan* p, int64_t cap);
 // spmv.cu
 int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
              const void* values, const void* x, void* y);

@@ -734,22 +734,38 @@ constexpr int ws_ctas_per_sm() {
   return (sizeof(T) == 8 || sizeof(I) == 8) ? kWsCtasPerSm - 1 : kWsCtasPerSm;
 }
 
-template <typename T, typename I, typename O>
-__global__ void __launch_bounds__(kWsWarps * 32, ws_ctas_per_sm<T, I>())
-spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
-                        const T* __restrict__ values, const O* __restrict__ perm,
-                        const T* __restrict__ x, T* __restrict__ y, const T alpha,
-                        const int64_t* __restrict__ starts, const int64_t stream_first,
-                        const int64_t num_streams, const int64_t rows,
-                        const int64_t nnz_end,
-                        int64_t* __restrict__ carry_row, T* __restrict__ carry_val,
-                        const __grid_constant__ ScatterArgs<T> sc) {
-  __shared__ __align__(16) T s_slab[kWsWarps][kWsChunk];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  T* slab = s_slab[warp];
-  const int64_t gw = int64_t(blockIdx.x) * kWsWarps + warp;
-  const int64_t nw = int64_t(gridDim.x) * kWsWarps;
+// The walk of one warp over its streams, shared by the two kernels below.  HUB: `colind`
+// is the plan's re-encoded copy (hub.cu) in which a reference to hub column number s reads
+// ~s (negative), and `hub` is the shared-window address of this CTA's copy of x at the
+// hub columns.
+template <typename T>
+__device__ __forceinline__ T ld_hub(uint32_t hub, int slot) {
+  // (a 32-bit shared address kept in one register: through a generic pointer the
+  // compiler rebuilds the shared window's base under every predicate)
+  if constexpr (sizeof(T) == 4) {
+    uint32_t r;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(hub + uint32_t(slot) * 4u));
+    return *reinterpret_cast<T*>(&r);
+  } else {
+    static_assert(sizeof(T) == 8, "4- or 8-byte element expected");
+    unsigned long long r;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(hub + uint32_t(slot) * 8u));
+    return *reinterpret_cast<T*>(&r);
+  }
+}
+
+template <typename T, typename I, typename O, bool HUB, int WARPS>
+__device__ __forceinline__ void
+ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
+                const T* __restrict__ values, const O* __restrict__ perm,
+                const T* __restrict__ x, T* __restrict__ y, const T alpha,
+                const int64_t* __restrict__ starts, const int64_t stream_first,
+                const int64_t num_streams, const int64_t rows, const int64_t nnz_end,
+                int64_t* __restrict__ carry_row, T* __restrict__ carry_val,
+                const ScatterArgs<T>& sc, const int lane, const int warp, T* slab,
+                const uint32_t hub) {
+  const int64_t gw = int64_t(blockIdx.x) * WARPS + warp;
+  const int64_t nw = int64_t(gridDim.x) * WARPS;
   const bool has_perm = perm != nullptr;
 
   for (int64_t s = stream_first + gw; s < stream_first + num_streams; s += nw) {
@@ -810,8 +826,12 @@ spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ coli
           }
           T xv[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            xv[j] = ld_ro(x + c.v[j]);
+          for (int j = 0; j < 4; ++j) {
+            if constexpr (HUB)
+              xv[j] = c.v[j] < I(0) ? ld_hub<T>(hub, int(~c.v[j])) : ld_ro(x + c.v[j]);
+            else
+              xv[j] = ld_ro(x + c.v[j]);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             p[u][j] = (kk + j >= k && kk + j < kend) ? v.v[j] * xv[j] : T(0);
@@ -915,6 +935,67 @@ spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ coli
       }
     }
   }
+}
+
+template <typename T, typename I, typename O>
+__global__ void __launch_bounds__(kWsWarps * 32, ws_ctas_per_sm<T, I>())
+spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
+                        const T* __restrict__ values, const O* __restrict__ perm,
+                        const T* __restrict__ x, T* __restrict__ y, const T alpha,
+                        const int64_t* __restrict__ starts, const int64_t stream_first,
+                        const int64_t num_streams, const int64_t rows,
+                        const int64_t nnz_end,
+                        int64_t* __restrict__ carry_row, T* __restrict__ carry_val,
+                        const __grid_constant__ ScatterArgs<T> sc) {
+  __shared__ __align__(16) T s_slab[kWsWarps][kWsChunk];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  ws_walk_streams<T, I, O, false, kWsWarps>(rowptr, colind, values, perm, x, y, alpha, starts,
+                                            stream_first, num_streams, rows, nnz_end,
+                                            carry_row, carry_val, sc, lane, warp, s_slab[warp],
+                                            0u);
+}
+
+// ============================================================================
+// Hub-stream kernel: the warp-stream walk with the most referenced columns of x held
+// in shared memory
+// ============================================================================
+// On a matrix with skewed COLUMN popularity (R-MAT: the 48 K most referenced of 16.7 M
+// columns take 44 % of the references) the warp-stream kernel is bound by the SM's
+// L1 -> L2 request port: one request per gather that misses L1, and a 28-200 KB L1 under
+// a 2 GB stream keeps few of them (hit rate 11 %).  Here the inspect phase (hub.cu)
+// counts the references per column, picks the top H, and re-encodes a plan-owned copy
+// of colind: a reference to hub number s is stored as ~s.  One CTA of 32 warps per SM
+// loads x at the H hub columns into shared memory once (H loads per CTA and launch
+// instead of one per reference), then runs the same walk; a negative index is a
+// shared-memory read, everything else the same gather as before.  Same arithmetic in
+// the same order as the warp-stream kernel: bit-identical y.
+constexpr int kHubWarps = 32; // one CTA per SM
+
+template <typename T, typename O>
+__global__ void __launch_bounds__(kHubWarps * 32, 1)
+spmv_hub_stream_kernel(const O* __restrict__ rowptr, const int32_t* __restrict__ hub_colind,
+                       const T* __restrict__ values, const O* __restrict__ perm,
+                       const T* __restrict__ x, T* __restrict__ y, const T alpha,
+                       const int64_t* __restrict__ starts, const int64_t stream_first,
+                       const int64_t num_streams, const int64_t rows,
+                       const int64_t nnz_end,
+                       int64_t* __restrict__ carry_row, T* __restrict__ carry_val,
+                       const __grid_constant__ ScatterArgs<T> sc,
+                       const int32_t* __restrict__ hub_cols, const int hub_n) {
+  extern __shared__ __align__(16) unsigned char hub_smem[];
+  T* slabs = reinterpret_cast<T*>(hub_smem);
+  T* hub = slabs + kHubWarps * kWsChunk;
+  for (int i = threadIdx.x; i < hub_n; i += kHubWarps * 32)
+    hub[i] = ld_ro(x + ld_stream(hub_cols + i));
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint32_t hub_addr = smem_u32(hub);
+  asm volatile("" : "+r"(hub_addr)); // one register, not a recomputation at every use
+  ws_walk_streams<T, int32_t, O, true, kHubWarps>(
+      rowptr, hub_colind, values, perm, x, y, alpha, starts, stream_first, num_streams, rows,
+      nnz_end, carry_row, carry_val, sc, lane, warp, slabs + warp * kWsChunk, hub_addr);
 }
 
 // ============================================================================
@@ -1217,12 +1298,43 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
 
   cudaError_t e = cudaSuccess;
   // the carry arrays and the unit count of the active partition
-  const bool ws = variant == kVariantWarpStream;
+  const bool hub = variant == kVariantHubStream;
+  const bool ws = variant == kVariantWarpStream || hub;
   const int64_t units = ws ? p->ws_streams : p->num_tiles;
   const int64_t* d_carry_row =
       static_cast<const int64_t*>(ws ? p->ws_carry_row.p : p->carry_row.p);
   const T* d_carry_val = static_cast<const T*>(ws ? p->ws_carry_val.p : p->carry_val.p);
-  if (ntiles > 0 && ws) {
+  if (ntiles > 0 && hub) {
+    if constexpr (sizeof(I) == 4) {
+      // one CTA per SM: the walk's slabs and the hub table fill the SM's shared memory
+      int64_t grid = (ntiles + kHubWarps - 1) / kHubWarps;
+      if (grid > int64_t(p->num_sms))
+        grid = p->num_sms;
+      const size_t smem =
+          (size_t(kHubWarps) * kWsChunk + size_t(p->hub_count)) * sizeof(T);
+      auto kern = spmv_hub_stream_kernel<T, O>;
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e != cudaSuccess)
+        return cuda_fail(p, e, "cudaFuncSetAttribute(spmv_hub_stream_kernel)");
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      // the encoded copy starts at the 16-byte aligned origin of the first stream
+      // (entry base & ~3 of the caller's array); the kernel indexes it absolutely
+      const int32_t* enc =
+          static_cast<const int32_t*>(p->hub_colind.p) - (p->base & ~int64_t(3));
+      kern<<<unsigned(grid), kHubWarps * 32, smem, p->stream>>>(
+          static_cast<const O*>(p->csr_rowptr), enc, static_cast<const T*>(values),
+          static_cast<const O*>(p->csr_perm), static_cast<const T*>(x), static_cast<T*>(y), a,
+          static_cast<const int64_t*>(p->ws_starts.p), T0, ntiles, p->csr_rows, nnz_end,
+          static_cast<int64_t*>(p->ws_carry_row.p), static_cast<T*>(p->ws_carry_val.p), sc,
+          static_cast<const int32_t*>(p->hub_cols.p), int(p->hub_count));
+      e = cudaGetLastError();
+      if (e != cudaSuccess)
+        return cuda_fail(p, e, "spmv_hub_stream_kernel");
+    } else {
+      return fail(p, SPBLAS_B200_NOT_SUPPORTED, "hub variant needs int32 column indices");
+    }
+  } else if (ntiles > 0 && ws) {
     int64_t grid = (ntiles + kWsWarps - 1) / kWsWarps;
     if (grid > int64_t(p->num_sms) * ws_ctas_per_sm<T, I>())
       grid = int64_t(p->num_sms) * ws_ctas_per_sm<T, I>();
@@ -1349,29 +1461,54 @@ int dispatch_index(spblas_b200_plan* p, int variant, const void* alpha, const vo
 // Arrays that are not 16-byte aligned fall back to the one-tile-per-CTA kernel.
 int prepare_spmv(spblas_b200_plan* p, int val_type, const void* values, int* variant,
                  const int64_t** starts, int64_t* units) {
-  int v = p->forced_variant >= 0
-              ? p->forced_variant
-              : (2 * p->uniform_tiles >= p->num_tiles ? kVariantPipelined : kVariantWarpStream);
+  const bool forced = p->forced_variant >= 0;
+  int v = forced ? p->forced_variant
+                 : (2 * p->uniform_tiles >= p->num_tiles ? kVariantPipelined : kVariantWarpStream);
+  // the hub variant is offered to matrices that would take the warp-stream kernel, on
+  // request (spblas_b200_plan_set_hub / SPBLAS_B200_HUB=1), for inspected plans only: the
+  // no-info overloads re-derive the structure on every call and cannot pay for the analysis
+  if (!forced && v == kVariantWarpStream && p->hub_enable && !p->light_inspect)
+    v = kVariantHubStream;
   if (!spmv_vec_ok(p, values))
     v = kVariantMergeTile;
-  if (v != kVariantMergeTile && v != kVariantPipelined && v != kVariantWarpStream)
+  if (v != kVariantMergeTile && v != kVariantPipelined && v != kVariantWarpStream &&
+      v != kVariantHubStream)
     v = kVariantMergeTile;
+  if (v == kVariantHubStream && (p->idx_type != SPBLAS_B200_I32 || p->host_exec_active))
+    v = kVariantWarpStream; // a negative index marks a hub; chunked launches reload the table
   if (p->num_tiles > int64_t(0x7fffffff))
     return fail(p, SPBLAS_B200_NOT_SUPPORTED, "too many tiles for one launch");
-  if (v == kVariantWarpStream && p->ws_streams < 0) {
+  if (v == kVariantHubStream) {
+    const int64_t cap = hub_capacity(p, type_size_val(val_type), kHubWarps);
+    if (p->hub_state == 0 || (p->hub_state == 1 && p->hub_cap != cap)) {
+      if (int rc = build_hub_table(p, cap))
+        return rc;
+      // not worth a CTA-wide table unless a fair share of the gathers leaves the L2 port
+      if (!forced && 20 * p->hub_refs < 3 * p->nnz) {
+        release(p->hub_colind);
+        release(p->hub_cols);
+        p->hub_state = -1;
+      }
+    }
+    if (p->hub_state != 1)
+      v = kVariantWarpStream;
+  }
+  const bool ws = v == kVariantWarpStream || v == kVariantHubStream;
+  if (ws && p->ws_streams < 0) {
     const bool wide = type_size_val(val_type) == 8 || p->idx_type == SPBLAS_B200_I64;
     const int64_t resident =
-        int64_t(p->num_sms) * (wide ? kWsCtasPerSm - 1 : kWsCtasPerSm) * kWsWarps;
+        v == kVariantHubStream
+            ? int64_t(p->num_sms) * kHubWarps
+            : int64_t(p->num_sms) * (wide ? kWsCtasPerSm - 1 : kWsCtasPerSm) * kWsWarps;
     if (int rc = build_ws_partition(p, resident))
       return rc;
   }
   p->spmv_variant = v;
   *variant = v;
   if (starts)
-    *starts = static_cast<const int64_t*>(v == kVariantWarpStream ? p->ws_starts.p
-                                                                  : p->tile_starts.p);
+    *starts = static_cast<const int64_t*>(ws ? p->ws_starts.p : p->tile_starts.p);
   if (units)
-    *units = v == kVariantWarpStream ? p->ws_streams : p->num_tiles;
+    *units = ws ? p->ws_streams : p->num_tiles;
   return SPBLAS_B200_SUCCESS;
 }
 

@@ -121,6 +121,29 @@ class operation_info_t:
     @property
     def barrier_timeout(self): return self._query_scalar(_cabi.Q_BARRIER_TIMEOUT)
 
+    # -- hub columns (include/spblas_b200.h: spblas_b200_plan_set_hub) ---------------------
+    @property
+    def hub_count(self): return self._query_scalar(_cabi.Q_HUB_COUNT)
+    @property
+    def hub_refs(self): return self._query_scalar(_cabi.Q_HUB_REFS)
+    @property
+    def hub_cols(self): return self._query_array(_cabi.Q_HUB_COLS, np.int32)
+    @property
+    def hub_colind(self): return self._query_array(_cabi.Q_HUB_COLIND, np.int32)
+
+    def set_hub(self, enable: bool = True, max_cols: int = 0, min_count: int = 0):
+        """Let the general SpMV path keep x at the most referenced columns in shared memory
+        (power-law matrices).  max_cols / min_count: 0 = the backend's defaults."""
+        st = _cabi.lib().spblas_b200_plan_set_hub(self._plan, 1 if enable else 0,
+                                                  int(max_cols), int(min_count))
+        _cabi.raise_for_status(st, self._err())
+
+    def force_spmv_variant(self, variant: int):
+        """Tuning / test knob: 0 merge-tile, 1 pipelined, 2 warp-stream, 3 hub-stream,
+        -1 automatic (spblas_b200_plan_force_variant)."""
+        st = _cabi.lib().spblas_b200_plan_force_variant(self._plan, int(variant))
+        _cabi.raise_for_status(st, self._err())
+
     # -- fused exchange (include/spblas_b200.h: set_scatter / set_barrier) ---------------
     def set_scatter(self, dsts=(), multicast: bool = False):
         """dsts: (device address of this block's row 0 in the destination, row_begin, row_end)
