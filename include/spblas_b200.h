@@ -171,11 +171,17 @@ SPBLAS_B200_API int spblas_b200_plan_cache_values(spblas_b200_plan* plan, int va
    is bound by the gathers of x that miss L1, not by HBM.  With enable != 0, a plan that
    would run the general (warp-stream) SpMV kernel counts the references per column on
    its first product, keeps the columns referenced at least min_count times (0 = twice
-   the SM count), takes the max_cols most referenced of them (0 = what the SM's shared
-   memory holds beside the kernel's own buffers: 49152 4-byte or 20480 8-byte values)
+   the SM count), takes the max_cols most referenced of them (0 = 32768 4-byte or 12288 8-byte
+   values: a 164 KB shared-memory carve-out, which leaves L1 the 92 KB the gathers in
+   flight need; at most 49152 / 20480, what the SM's shared memory holds)
    and stores a re-encoded copy of colind (nnz * 4 bytes, owned by the plan); the hub
    kernel then reads x at those columns from shared memory.  Used only if at least 15 %
    of the stored entries reference a hub; results are bit-identical to the plain kernel's.
+   max_cols / min_count = -1 leave the current setting unchanged.  The C++ headers call
+   set_hub(1, -1, -1) from multiply_inspect when the operand is wrapped in matrix_opt —
+   the reference's marker for "the backend may keep optimised state for this matrix"
+   (views/matrix_opt_impl.hpp:14-93).  Measured on R-MAT scale 24, fp32 (C4): 1.13 ms ->
+   1.03 ms; the analysis costs about 40 products, once.
    int32 column indices only; plans inspected through multiply_inspect only (the no-info
    overloads never analyse).  Also read from the environment at plan creation:
    SPBLAS_B200_HUB, SPBLAS_B200_HUB_COLS, SPBLAS_B200_HUB_MIN_COUNT.  No reference

@@ -196,6 +196,8 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->ws_carveout = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_HUB"))
     p->hub_enable = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SPBLAS_B200_HUB_PREFETCH"))
+    p->hub_prefetch = std::atoi(v) != 0;
   if (const char* v = std::getenv("SPBLAS_B200_HUB_COLS"))
     p->hub_cap_override = std::max<long long>(0, std::atoll(v));
   if (const char* v = std::getenv("SPBLAS_B200_HUB_MIN_COUNT"))
@@ -294,9 +296,13 @@ int spblas_b200_plan_set_hub(spblas_b200_plan* p, int enable, int64_t max_cols,
   if (!p)
     return SPBLAS_B200_INVALID_ARGUMENT;
   p->err.clear();
-  if (max_cols < 0 || min_count < 0)
-    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "negative hub parameter");
+  if (max_cols < -1 || min_count < -1)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "bad hub parameter");
   p->hub_enable = enable ? 1 : 0;
+  if (max_cols < 0)
+    max_cols = p->hub_cap_override; // -1: keep
+  if (min_count < 0)
+    min_count = p->hub_min_count;
   if (p->hub_cap_override != max_cols || p->hub_min_count != min_count)
     p->hub_state = 0; // the table (if any) was built under other limits
   p->hub_cap_override = max_cols;

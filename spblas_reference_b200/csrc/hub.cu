@@ -101,16 +101,22 @@ struct Scratch { // freed when the analysis returns, however it returns
 
 } // namespace
 
-// How many columns of x the hub kernel can hold: the SM's shared memory minus the
-// walk's per-warp slabs (256 entries each), in whole 1024-column steps.
+// How many columns of x the hub kernel holds.  The hardware limit is the SM's shared
+// memory minus the walk's per-warp slabs (256 entries each); the DEFAULT stops at a
+// 164 KB carve-out, because every gather in flight occupies an L1 line and L1 is what
+// shared memory leaves of the SM's 256 KB array: on R-MAT scale 24 (fp32) 32768 columns
+// (164 KB carve-out, 92 KB L1) run in 1.03 ms, 40960 in 1.08 ms, 49152 (228 KB, 28 KB L1)
+// in 1.76 ms — slower than no table at all (1.13 ms).  Whole 1024-column steps.
 int64_t hub_capacity(const spblas_b200_plan* p, size_t val_bytes, int walk_warps) {
-  const int64_t budget = int64_t(p->smem_per_sm) - 1024; // per-CTA limit: 1 KB is the system's
   const int64_t slabs = int64_t(walk_warps) * 256 * int64_t(val_bytes);
-  int64_t cap = (budget - slabs) / int64_t(val_bytes);
-  cap = cap > 0 ? (cap / 1024) * 1024 : 0;
-  if (p->hub_cap_override > 0 && p->hub_cap_override < cap)
-    cap = p->hub_cap_override;
-  return cap;
+  const auto columns = [&](int64_t budget) {
+    const int64_t c = (budget - slabs) / int64_t(val_bytes);
+    return c > 0 ? (c / 1024) * 1024 : int64_t(0);
+  };
+  const int64_t hw = columns(int64_t(p->smem_per_sm) - 1024); // per-CTA limit: 1 KB is the system's
+  if (p->hub_cap_override > 0)
+    return p->hub_cap_override < hw ? p->hub_cap_override : hw;
+  return std::min(hw, columns(int64_t(163) * 1024));
 }
 
 int build_hub_table(spblas_b200_plan* p, int64_t cap) {

@@ -754,7 +754,10 @@ __device__ __forceinline__ T ld_hub(uint32_t hub, int slot) {
   }
 }
 
-template <typename T, typename I, typename O, bool HUB, int WARPS>
+// PF: the column indices of the NEXT chunk are loaded at the top of every step (8 more
+// registers for 4-byte indices), so that their trip to HBM overlaps this chunk's gathers
+// and row sums instead of opening the next step.
+template <typename T, typename I, typename O, bool HUB, int WARPS, bool PF = false>
 __device__ __forceinline__ void
 ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
                 const T* __restrict__ values, const O* __restrict__ perm,
@@ -791,8 +794,24 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
     T carry = T(0);            // lane 0: that part's sum over the chunks already done
     int k = cur;
     int kb = 0;
+    [[maybe_unused]] Quad<I> pf[2];
+    [[maybe_unused]] bool pf_ok[2] = {false, false};
     do {
       const int kend = kb + kWsChunk < k_e ? kb + kWsChunk : k_e;
+      [[maybe_unused]] Quad<I> now[2];
+      [[maybe_unused]] bool now_ok[2] = {false, false};
+      if constexpr (PF) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          now[u] = pf[u];
+          now_ok[u] = pf_ok[u];
+          // a whole quad of the next chunk, inside the stream and inside the arrays
+          const int kn = kb + kWsChunk + 4 * (lane + 32 * u);
+          pf_ok[u] = kn < k_e && kn + 4 <= arr_end;
+          if (pf_ok[u])
+            pf[u] = ld_stream_quad(ci + kn);
+        }
+      }
       // ---- products of this chunk: two quads per lane -----------------------------
       T p[2][4];
 #pragma unroll
@@ -805,7 +824,14 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
           Quad<I> c;
           Quad<T> v;
           if (kk + 4 <= arr_end) {
-            c = ld_stream_quad(ci + kk);
+            if constexpr (PF) {
+              if (now_ok[u])
+                c = now[u];
+              else
+                c = ld_stream_quad(ci + kk);
+            } else {
+              c = ld_stream_quad(ci + kk);
+            }
             if (!has_perm) {
               v = ld_stream_quad(va + kk);
             } else {
@@ -972,7 +998,7 @@ spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ coli
 // the same order as the warp-stream kernel: bit-identical y.
 constexpr int kHubWarps = 32; // one CTA per SM
 
-template <typename T, typename O>
+template <typename T, typename O, bool PF>
 __global__ void __launch_bounds__(kHubWarps * 32, 1)
 spmv_hub_stream_kernel(const O* __restrict__ rowptr, const int32_t* __restrict__ hub_colind,
                        const T* __restrict__ values, const O* __restrict__ perm,
@@ -993,7 +1019,7 @@ spmv_hub_stream_kernel(const O* __restrict__ rowptr, const int32_t* __restrict__
   const int warp = threadIdx.x >> 5;
   uint32_t hub_addr = smem_u32(hub);
   asm volatile("" : "+r"(hub_addr)); // one register, not a recomputation at every use
-  ws_walk_streams<T, int32_t, O, true, kHubWarps>(
+  ws_walk_streams<T, int32_t, O, true, kHubWarps, PF>(
       rowptr, hub_colind, values, perm, x, y, alpha, starts, stream_first, num_streams, rows,
       nnz_end, carry_row, carry_val, sc, lane, warp, slabs + warp * kWsChunk, hub_addr);
 }
@@ -1312,12 +1338,21 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
         grid = p->num_sms;
       const size_t smem =
           (size_t(kHubWarps) * kWsChunk + size_t(p->hub_count)) * sizeof(T);
-      auto kern = spmv_hub_stream_kernel<T, O>;
+      auto kern = p->hub_prefetch ? spmv_hub_stream_kernel<T, O, true>
+                                  : spmv_hub_stream_kernel<T, O, false>;
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
       if (e != cudaSuccess)
         return cuda_fail(p, e, "cudaFuncSetAttribute(spmv_hub_stream_kernel)");
-      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           cudaSharedmemCarveoutMaxShared);
+      // exactly what the slabs and the table need: the rest of the SM's array stays L1,
+      // and every gather in flight holds an L1 line — with the smallest L1 (28 KB, 224
+      // lines) the misses in flight, not the port, bound the kernel (measured: slower
+      // than the plain walk with 56 % of the gathers served from shared memory)
+      int carve = p->ws_carveout;
+      if (carve < 0) {
+        carve = int(((smem + 1024) * 100 + p->smem_per_sm - 1) / p->smem_per_sm);
+        carve = carve > 100 ? 100 : carve;
+      }
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
       // the encoded copy starts at the 16-byte aligned origin of the first stream
       // (entry base & ~3 of the caller's array); the kernel indexes it absolutely
       const int32_t* enc =

@@ -133,7 +133,7 @@ class operation_info_t:
 
     def set_hub(self, enable: bool = True, max_cols: int = 0, min_count: int = 0):
         """Let the general SpMV path keep x at the most referenced columns in shared memory
-        (power-law matrices).  max_cols / min_count: 0 = the backend's defaults."""
+        (power-law matrices).  max_cols / min_count: 0 = the backend's defaults, -1 = keep."""
         st = _cabi.lib().spblas_b200_plan_set_hub(self._plan, 1 if enable else 0,
                                                   int(max_cols), int(min_count))
         _cabi.raise_for_status(st, self._err())
@@ -234,6 +234,11 @@ def _inspect(info: operation_info_t, a, x, y, flags=_cabi.INSPECT_DEFAULT):
             plan, fmt, a_base.shape[0], a_base.shape[1], a_base.nnz, ptr.data_ptr(),
             ind.data_ptr(), index_type(ptr), index_type(ind), k_hint, flags)
     _cabi.raise_for_status(st, info._err())
+    if has_matrix_opt(a) and flags == _cabi.INSPECT_DEFAULT:
+        # ... and structure-only state: x at the most referenced columns in shared memory,
+        # decided on the first product (spblas_b200_plan_set_hub; bit-identical results)
+        st = _cabi.lib().spblas_b200_plan_set_hub(plan, 1, -1, -1)
+        _cabi.raise_for_status(st, info._err())
     if has_matrix_opt(a) and fmt == _cabi.CSC and flags == _cabi.INSPECT_DEFAULT:
         # matrix_opt: the backend may keep optimised, value-dependent state (the reference's
         # oneMKL backend calls optimize_gemv under the same condition) — here the values

@@ -7,7 +7,6 @@ shards with unaligned bases, CSC operands, and the automatic choice.
 
 (The file name sorts last on purpose: a new kernel is tested after everything that was
 already green.)"""
-import os
 import zlib
 
 import numpy as np
@@ -17,14 +16,7 @@ import torch
 import spblas_reference_b200 as sb
 from helpers import assert_rows_within_bound, csc_on_device, csr_on_device, dev
 
-pytestmark = [
-    pytest.mark.gpu,
-    # written in a session that had no GPU time left: set SPBLAS_B200_RUN_UNVALIDATED=1 to run
-    # them; the gate goes away with the first green run on a B200
-    pytest.mark.skipif(os.environ.get("SPBLAS_B200_RUN_UNVALIDATED") != "1",
-                       reason="hub variant not yet validated on a GPU "
-                              "(SPBLAS_B200_RUN_UNVALIDATED=1 runs it)"),
-]
+pytestmark = pytest.mark.gpu
 
 
 def _skewed_csr(rng, m, n, lens, vt, ot=np.int32, power=4.0):
@@ -171,8 +163,8 @@ def test_hub_automatic_choice(cuda, oracle):
     y_ws, i_ws = _run(a, xd, m, None)
     assert i_ws.spmv_variant == 2 and i_ws.hub_count == 0
     y_hub, i_hub = _run(a, xd, m, None, hub=(0, 4))
-    assert i_hub.spmv_variant == 3 and 0 < i_hub.hub_count <= 49152
-    hubs, refs, _ = oracle.hub_columns(ci, n, 49152, 4)
+    assert i_hub.spmv_variant == 3 and 0 < i_hub.hub_count <= 32768
+    hubs, refs, _ = oracle.hub_columns(ci, n, 32768, 4)
     assert i_hub.hub_count == len(hubs) and i_hub.hub_refs == refs
     assert torch.equal(y_ws, y_hub)
     # the no-info overload (a light inspect per call, never analysed): the plain walk's result
@@ -192,7 +184,7 @@ def test_hub_automatic_choice(cuda, oracle):
     assert i64.spmv_variant == 2 and torch.equal(y64, y_ws)
     # a stencil keeps the TMA pipeline
     from spblas_reference_b200 import generators as G
-    vs, rps, cis, shape = G.poisson2d_csr(96, torch.float64, cuda)
+    vs, rps, cis, shape = G.poisson2d_csr(1024, torch.float64, cuda)   # (a small grid's tiles mix 4- and 5-entry rows)
     st = sb.csr_view(vs, rps, cis, shape, int(cis.numel()))
     xs = torch.ones(shape[1], dtype=torch.float64, device=cuda)
     _, i_st = _run(st, xs, shape[0], None, hub=(0, 1))
@@ -202,8 +194,10 @@ def test_hub_automatic_choice(cuda, oracle):
 
 
 def test_hub_default_capacity_and_value_width_switch(cuda, oracle, monkeypatch):
-    """Default limits on a matrix large enough to fill the table: at most 49152 columns for
-    4-byte values, 20480 for 8-byte ones; the table is rebuilt when the value width changes."""
+    """Default limits on a matrix large enough to fill the table: 32768 columns for 4-byte
+    values, 12288 for 8-byte ones (a 164 KB carve-out; L1 keeps the rest); the table is
+    rebuilt when the value width changes; an explicit max_cols may go up to what the SM's
+    shared memory holds (49152 / 20480)."""
     # (the stream length follows the number of resident warps, which differs between the two
     # kernels; pinned so that both cut the rows at the same places and agree bit for bit)
     monkeypatch.setenv("SPBLAS_B200_WS_ITEMS", "1024")
@@ -215,8 +209,8 @@ def test_hub_default_capacity_and_value_width_switch(cuda, oracle, monkeypatch):
     x32 = dev(x)
     y_ws, i_ws = _run(a32, x32, m, 2)
     y_hub, info = _run(a32, x32, m, 3, hub=(0, 8))
-    hubs, refs, enc = oracle.hub_columns(ci, n, 49152, 8)
-    assert info.hub_count == len(hubs) == 49152 and info.hub_refs == refs
+    hubs, refs, enc = oracle.hub_columns(ci, n, 32768, 8)
+    assert info.hub_count == len(hubs) == 32768 and info.hub_refs == refs
     assert np.array_equal(info.hub_cols, hubs) and np.array_equal(info.hub_colind, enc)
     assert torch.equal(y_ws, y_hub)
     # the same plan, fp64 values: smaller table
@@ -225,13 +219,17 @@ def test_hub_default_capacity_and_value_width_switch(cuda, oracle, monkeypatch):
     y64 = torch.empty(m, dtype=torch.float64, device=cuda)
     sb.multiply_execute(info, a64, x64, y64)
     torch.cuda.synchronize()
-    hubs64, refs64, enc64 = oracle.hub_columns(ci, n, 20480, 8)
-    assert info.spmv_variant == 3 and info.hub_count == 20480 and info.hub_refs == refs64
+    hubs64, refs64, enc64 = oracle.hub_columns(ci, n, 12288, 8)
+    assert info.spmv_variant == 3 and info.hub_count == 12288 and info.hub_refs == refs64
     assert np.array_equal(info.hub_cols, hubs64) and np.array_equal(info.hub_colind, enc64)
     y_ref = oracle.spmv("csr", (m, n), rp, ci, v.astype(np.float64), x.astype(np.float64))
     assert_rows_within_bound(y64.cpu().numpy(), y_ref, rp,
                              oracle.abs_rowsum(rp, ci, v.astype(np.float64), x.astype(np.float64)),
                              "hub fp64 after fp32")
+    # an explicit request is clamped to the hardware limit, not to the default
+    y_max, i_max = _run(a32, x32, m, 3, hub=(1 << 20, 8))
+    assert i_max.hub_count == 49152 and torch.equal(y_max, y_ws)
+    i_max.close()
     i_ws.close()
     info.close()
 
