@@ -2,7 +2,7 @@
 """bench.py — the measurement contract for the spblas B200 backend.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload c2|c1|c4|c3k32|c3k128]
+                    [--workload c2|c1|c4|c3k32|c3k128|c5|c5mm|c1t|c4t|t1|t4|trsv]
 
 Workload at N=1 (the configuration BASELINE.json's metric is quoted on, configs[1]):
   C2 — 2D Poisson 5-point stencil on a 4096 x 4096 grid, CSR SpMV in fp64 with int32
@@ -43,9 +43,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2",
-                    choices=["c1", "c2", "c3k32", "c3k128", "c4", "c5", "t1", "t4", "c1t", "c4t", "trsv"])
+                    choices=["c1", "c2", "c3k32", "c3k128", "c4", "c5", "c5mm", "t1", "t4", "c1t",
+                             "c4t", "trsv"])
     ap.add_argument("--scale", type=int, default=0,
-                    help="C5 R-MAT scale (default 24 + log2(N): 16.7M rows per GPU)")
+                    help="C5 R-MAT scale (default 24 + log2(N): 16.7M rows per GPU; c5mm: "
+                         "22 + log2(N))")
     ap.add_argument("--grid", type=int, default=4096, help="C2 grid edge (per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -255,6 +257,13 @@ def main():
         from bench_extra import run_c5   # R-MAT fp64 / int64 offsets, nnz-balanced row blocks
         run_c5(args, sb, G, dev, peak, peak_src, ClockSampler(local_rank), world, rank,
                barrier, max_over_ranks, sum_over_ranks)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    if args.workload == "c5mm":
+        from bench_extra import run_c5mm  # R-MAT fp64 SpMM, row blocks, B replicated, no exchange
+        run_c5mm(args, sb, G, dev, peak, peak_src, ClockSampler(local_rank), world, rank,
+                 barrier, max_over_ranks, sum_over_ranks)
         if world > 1:
             dist.destroy_process_group()
         return

@@ -192,7 +192,14 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         v, rp, ci, shape = G.rmat_csr(24, 16, seed=24, dtype=torch.float32, device=dev)
         m, n = shape
         nnz = int(ci.numel())
-        a = sb.csr_view(v, rp, ci, shape, nnz)
+        a_plain = sb.csr_view(v, rp, ci, shape, nnz)
+        name = "C4 R-MAT scale 24 (edge factor 16) CSR SpMV fp32/int32"
+        a = a_plain
+        if os.environ.get("SPBLAS_B200_MATRIX_OPT", "1") != "0":
+            # matrix_opt: the plan may keep structure-derived state — here x at the most
+            # referenced columns in shared memory (hub variant); =0 measures the plain walk
+            a = sb.matrix_opt(a_plain)
+            name += ", matrix_opt (hub columns of x in shared memory)"
         x = G.dense_uniform((n,), 5, torch.float32, dev)
         y = torch.empty(m, device=dev)
         t0 = time.perf_counter()
@@ -201,11 +208,28 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         extra["inspect_ms"] = (time.perf_counter() - t0) * 1e3
         extra["max_row_len"] = info.max_row_len
         extra["empty_rows"] = info.empty_rows
+        t0 = time.perf_counter()
+        sb.multiply_execute(info, a, x, y)           # first product: builds the lazy tables
+        torch.cuda.synchronize()
+        extra["first_execute_ms"] = (time.perf_counter() - t0) * 1e3
+        extra["spmv_variant"] = info.spmv_variant
+        extra["hub_columns"] = info.hub_count
+        extra["hub_reference_share"] = info.hub_refs / max(nnz, 1)
 
         def fn(i):
             sb.multiply_execute(info, a, x, y)
+
+        def plain_walk_ms():
+            """the same product without matrix_opt (warp-stream kernel), for the A/B"""
+            y2 = torch.empty_like(y)
+            info2 = sb.multiply_inspect(a_plain, x, y2)
+            ms2 = _time_loop(lambda i: sb.multiply_execute(info2, a_plain, x, y2), K, W)
+            same = bool(torch.equal(y, y2))
+            v2 = info2.spmv_variant
+            info2.close()
+            return {"ms": ms2, "spmv_variant": v2, "bit_identical_to_headline": same}
+        side_measurements = {"plain_walk": plain_walk_ms} if a is not a_plain else {}
         flops, nbytes, dtype = 2.0 * nnz, _bytes_spmv(nnz, m, n, 4), "f32"
-        name = "C4 R-MAT scale 24 (edge factor 16) CSR SpMV fp32/int32"
         extra["l2_policy"] = "inputs larger than L2 (2.3 GB)"
         launches_of = lambda: info.total_launches
         cmp_args = ("spmv", [(m, n, rp, ci, v, x, torch.empty_like(y))], 1.0)
@@ -245,6 +269,11 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
         torch.cuda.synchronize()
     clocks = sampler.stop()
     clocks["window"] = "the timed region plus 0.6 s of the same loop right after it"
+    for key, measure in locals().get("side_measurements", {}).items():
+        try:
+            extra[key] = measure()
+        except Exception as exc:                       # a side number never costs the line
+            extra[key] = {"error": repr(exc)}
     achieved = nbytes / (ms * 1e-3) / 1e9
     from bench import ncu_traffic
     traffic = ncu_traffic(wl)
@@ -526,5 +555,98 @@ def run_c5(args, sb, G, dev, peak, peak_src, sampler, world, rank, barrier, max_
                                  "sector each: the compulsory-bytes roofline is not reachable "
                                  "(SURVEY 8d caveat)"},
             "clocks": clocks, "gpu_launches": launches,
+        }
+        print(json.dumps(line), flush=True)
+
+
+def run_c5mm(args, sb, G, dev, peak, peak_src, sampler, world, rank, barrier, max_over_ranks,
+             sum_over_ranks):
+    """C5's SpMM half (BASELINE.json configs[4]): R-MAT (edge factor 16) CSR times a dense
+    row-major B with k = 32 in fp64, int32 indices, int64 offsets, nnz-balanced row blocks
+    over the ranks, B replicated.  A single product C = A B needs no exchange (SURVEY 8e:
+    every rank writes its own block of C), so the step has no collective; time = max over
+    ranks.  Weak-scaled: scale = 22 + log2(N) by default (B is k times an x: 8.6 GB at scale
+    25); --scale 27 is BASELINE's size (34 GB of B per GPU)."""
+    import math
+    from spblas_reference_b200.sharded import balanced_nnz_blocks
+    K, W = max(1, args.steps), max(3, args.warmup)
+    k = 32
+    scale = args.scale if args.scale > 0 else 22 + int(round(math.log2(world)))
+    n = 1 << scale
+    deg = G.rmat_degrees(scale, 16, seed=27, device=dev)
+    rowptr_all = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(deg, 0, out=rowptr_all[1:])
+    blocks = balanced_nnz_blocks(rowptr_all, world)
+    del deg, rowptr_all
+    r0, r1 = blocks[rank]
+    v, rp, ci, shape = G.rmat_csr(scale, 16, seed=27, dtype=torch.float64, device=dev,
+                                  off_dtype=torch.int64, row_begin=r0, row_end=r1)
+    m_loc, nnz_loc = shape[0], int(ci.numel())
+    a = sb.csr_view(v, rp, ci, shape, nnz_loc)
+    B = G.dense_uniform_rows(n, k, 6, torch.float64, dev)
+    C = torch.empty((m_loc, k), dtype=torch.float64, device=dev)
+    t0 = time.perf_counter()
+    info = sb.multiply_inspect(a, B, C)
+    torch.cuda.synchronize()
+    inspect_ms = (time.perf_counter() - t0) * 1e3
+
+    def fn(i):
+        sb.multiply_execute(info, a, B, C)
+    for i in range(W):
+        fn(i)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = info.total_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        fn(i)
+    e1.record()
+    barrier()
+    step_ms = max_over_ranks(e0.elapsed_time(e1) / K)
+    launches = int(sum_over_ranks(info.total_launches - l0))
+    clocks = None
+    if rank == 0:
+        t_load = time.perf_counter()        # the same load a little longer for the 100 ms sampler
+        while time.perf_counter() - t_load < 0.6:
+            for i in range(5):
+                fn(i)
+            torch.cuda.synchronize()
+        clocks = sampler.stop()
+        clocks["window"] = "the timed region plus 0.6 s of the same loop on rank 0 right after it"
+    barrier()
+    total_nnz = int(sum_over_ranks(nnz_loc))
+    nbytes = nnz_loc * 12 + (m_loc + 1) * 8 + n * k * 8 + m_loc * k * 8   # B fully replicated
+    achieved = nbytes / (step_ms * 1e-3) / 1e9
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline("spmm", m_loc, n, rp, ci, v, B, None, 100_000, 2.0 * k,
+                           f"C5 SpMM k={k} row block")
+    if rank == 0:
+        line = {
+            "metric": "CSR SpMM GFLOP/s", "value": 2.0 * total_nnz * k / (step_ms * 1e-3) / 1e9,
+            "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"C5 R-MAT scale {scale} (edge factor 16) CSR SpMM fp64, k={k}, "
+                                   "int32 indices, int64 offsets, nnz-balanced row blocks, B "
+                                   "replicated, single product (no exchange)",
+                       "nnz": total_nnz, "rows_rank0": m_loc, "nnz_rank0": nnz_loc,
+                       "parallelism": f"rowblock{world}", "exchange": "none",
+                       "inspect_ms": inspect_ms, "spmm_variant": info.spmm_variant,
+                       "num_segments": info.num_segments, "max_row_len": info.max_row_len,
+                       "l2_policy": "inputs larger than L2"},
+            "gbs": achieved,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
+                         "gather_model_bytes": nnz_loc * 12 + (m_loc + 1) * 8 + nnz_loc * k * 8
+                         + m_loc * k * 8,
+                         "note": "random 256-byte rows of B: the compulsory-bytes roofline is "
+                                 "not reachable (SURVEY 8d caveat); the gather model counts one "
+                                 "row of B per stored entry"},
+            "clocks": clocks, "gpu_launches": launches, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

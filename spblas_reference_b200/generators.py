@@ -55,6 +55,25 @@ def dense_uniform(shape, seed: int, dtype, device) -> torch.Tensor:
     return hash_uniform(seed, idx, dtype).reshape(shape)
 
 
+def dense_uniform_rows(rows: int, cols: int, seed: int, dtype, device,
+                       chunk_elems: int = 1 << 26) -> torch.Tensor:
+    """dense_uniform((rows, cols), ...) filled in row chunks: the same values, with
+    temporaries of chunk_elems elements instead of the whole operand's size (a replicated
+    SpMM operand of tens of GB must not triple its footprint while it is generated)."""
+    out = torch.empty((rows, cols), dtype=dtype, device=device)
+    step = max(1, chunk_elems // max(cols, 1))
+    for r0 in range(0, rows, step):
+        r1 = min(rows, r0 + step)
+        idx = torch.arange(r0 * cols, r1 * cols, dtype=torch.int64, device=device)
+        if dtype == torch.int32:
+            blk = (_lsr(splitmix64(idx + _c64(seed * 0x632BE59BD9B4E019)), 60) - 8).to(torch.int32)
+        else:
+            blk = hash_uniform(seed, idx, dtype)
+        out[r0:r1] = blk.reshape(r1 - r0, cols)
+        del idx, blk
+    return out
+
+
 # -------------------------------------------------------------------------------------
 def poisson2d_csr(g: int, dtype=torch.float64, device="cpu", row_begin: int = 0,
                   row_end: Optional[int] = None, off_dtype=torch.int32,

@@ -104,3 +104,31 @@ def test_host_execute_argument_checks():
         sb.multiply_execute_host(None, a, torch.zeros(4), torch.zeros(3))
     with pytest.raises(RuntimeError, match="device memory"):      # A itself must be on the device
         sb.multiply_execute_host(info, a, torch.zeros(4), torch.zeros(3))
+
+
+def test_dense_operand_generated_in_chunks_is_the_same_operand():
+    """bench.py --workload c5mm fills its replicated B in row chunks (tens of GB must not
+    triple their footprint while generated): same values as the one-shot generator."""
+    from spblas_reference_b200 import generators as G
+    for dt in (torch.float64, torch.float32, torch.int32):
+        whole = G.dense_uniform((1000, 32), 6, dt, "cpu")
+        parts = G.dense_uniform_rows(1000, 32, 6, dt, "cpu", chunk_elems=5000)
+        assert torch.equal(whole, parts)
+
+
+def test_hub_column_definition_known_answer(oracle):
+    """oracle.hub_columns — the definition the GPU analysis (csrc/hub.cu) is compared with
+    bit for bit: columns referenced >= min_count times, the max_cols most referenced (ties:
+    smaller column first), renumbered ascending; a reference to hub s is re-encoded as ~s."""
+    import numpy as np
+    ci = np.array([5, 5, 5, 2, 2, 9, 9, 9, 9, 1, 0, 2], dtype=np.int32)
+    hubs, refs, enc = oracle.hub_columns(ci, 10, 2, 2)      # counts: 9 -> 4, 2 -> 3, 5 -> 3
+    assert hubs.tolist() == [2, 9] and refs == 7
+    assert enc.tolist() == [5, 5, 5, -1, -1, -2, -2, -2, -2, 1, 0, -1]
+    hubs, refs, enc = oracle.hub_columns(ci, 10, 8, 3)
+    assert hubs.tolist() == [2, 5, 9] and refs == 10
+    assert enc.tolist() == [-2, -2, -2, -1, -1, -3, -3, -3, -3, 1, 0, -1]
+    hubs, refs, enc = oracle.hub_columns(ci, 10, 8, 5)      # nothing is referenced 5 times
+    assert len(hubs) == 0 and refs == 0 and enc.tolist() == ci.tolist()
+    hubs, refs, enc = oracle.hub_columns(np.array([], dtype=np.int32), 4, 8, 1)
+    assert len(hubs) == 0 and refs == 0 and len(enc) == 0
