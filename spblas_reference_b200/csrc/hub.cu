@@ -102,11 +102,11 @@ struct Scratch { // freed when the analysis returns, however it returns
 } // namespace
 
 // How many columns of x the hub kernel holds.  The hardware limit is the SM's shared
-// memory minus the walk's per-warp slabs (256 entries each); the DEFAULT stops at a
-// 164 KB carve-out, because every gather in flight occupies an L1 line and L1 is what
-// shared memory leaves of the SM's 256 KB array: on R-MAT scale 24 (fp32) 32768 columns
-// (164 KB carve-out, 92 KB L1) run in 1.03 ms, 40960 in 1.08 ms, 49152 (228 KB, 28 KB L1)
-// in 1.76 ms — slower than no table at all (1.13 ms).  Whole 1024-column steps.
+// memory minus the walk's per-warp slabs (256 entries each); the DEFAULT stops at 163 KB
+// of shared memory, because every gather in flight occupies an L1 line and L1 is what
+// shared memory leaves of the SM's unified array: on R-MAT scale 24 (fp32) 32768 columns
+// (160 KB) run in 1.03 ms, 40960 (192 KB) in 1.08 ms, 49152 (224 KB) in 1.76 ms — slower
+// than no table at all (1.13 ms).  Whole 1024-column steps.
 int64_t hub_capacity(const spblas_b200_plan* p, size_t val_bytes, int walk_warps) {
   const int64_t slabs = int64_t(walk_warps) * 256 * int64_t(val_bytes);
   const auto columns = [&](int64_t budget) {
