@@ -68,7 +68,8 @@ void release_all(spblas_b200_plan* p) {
                           &p->spmm_carry_row, &p->spmm_carry_val, &p->barrier_state,
                           &p->ws_starts, &p->ws_carry_row, &p->ws_carry_val, &p->own_values,
                           &p->trsv_level, &p->trsv_order, &p->trsv_tmp0, &p->trsv_tmp1,
-                          &p->trsv_level_ptr, &p->hub_cols, &p->hub_colind};
+                          &p->trsv_level_ptr, &p->hub_cols, &p->hub_colind,
+                          &p->trsv_row_ready, &p->trsv_state};
   for (DeviceBuffer* b : bufs)
     release(*b);
   release(p->hc_colmax);
@@ -204,6 +205,10 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->hub_min_count = std::max<long long>(0, std::atoll(v));
   if (const char* v = std::getenv("SPBLAS_B200_TRSV_INSPECT"))
     p->trsv_relax_inspect = std::string(v) == "relax";
+  if (const char* v = std::getenv("SPBLAS_B200_TRSV_PERSISTENT"))
+    p->trsv_persistent = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SPBLAS_B200_TRSV_CTAS_PER_SM"))
+    p->trsv_persistent_ctas = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_TRSV_GRAPH"))
     p->trsv_use_graph = std::atoi(v) != 0;
   if (const char* v = std::getenv("SPBLAS_B200_HOST_CHUNKS"))
@@ -617,6 +622,15 @@ int spblas_b200_plan_query(spblas_b200_plan* p, int what, void* out,
       B200_CUDA_TRY(p, cudaStreamSynchronize(p->stream));
     }
     return scalar(int64_t(st[1]));
+  }
+  case SPBLAS_B200_Q_TRSV_TIMEOUT: {
+    unsigned int st = 0;
+    if (p->trsv_state.p) {
+      B200_CUDA_TRY(p, cudaMemcpyAsync(&st, p->trsv_state.p, sizeof(st), cudaMemcpyDeviceToHost,
+                                       p->stream));
+      B200_CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    }
+    return scalar(int64_t(st));
   }
   case SPBLAS_B200_Q_TRSV_LEVELS:
     return scalar(p->trsv_ready ? p->trsv_levels : 0);

@@ -129,6 +129,13 @@ struct spblas_b200_plan {
   cudaGraphExec_t trsv_graph[2] = {nullptr, nullptr};
   cudaStream_t trsv_capture_stream = nullptr;
   b200::DeviceBuffer trsv_params;        // operands of the current solve, read by the graph's kernels
+  // one persistent launch in level order with per-row ready flags (trsv_persistent_kernel):
+  // env SPBLAS_B200_TRSV_PERSISTENT=1; not the default until measured on a B200
+  bool trsv_persistent = false;
+  int trsv_persistent_ctas = 0;          // env SPBLAS_B200_TRSV_CTAS_PER_SM (0: what fits)
+  int trsv_epoch = 0;                    // solves so far: the value a row's flag takes when x_i is final
+  b200::DeviceBuffer trsv_row_ready;        // int32 per row: epoch of the solve that last wrote x_i
+  b200::DeviceBuffer trsv_state;         // uint32: 1 if a row gave up waiting for a dependency
 
   // ---- merge-path partition --------------------------------------------------
   int tile_items = b200::kSpmvTileItems;

@@ -115,6 +115,8 @@ class operation_info_t:
     def trsv_levels(self): return self._query_scalar(_cabi.Q_TRSV_LEVELS)
     @property
     def trsv_sweeps(self): return self._query_scalar(_cabi.Q_TRSV_SWEEPS)
+    @property
+    def trsv_timeout(self): return self._query_scalar(_cabi.Q_TRSV_TIMEOUT)
 
     @property
     def barrier_epoch(self): return self._query_scalar(_cabi.Q_BARRIER_EPOCH)

@@ -1,0 +1,76 @@
+"""GPU tests of code written after this round's GPU time was spent: they have never run.
+SPBLAS_B200_RUN_UNVALIDATED=1 runs them; each moves to its proper file with its first green
+run on a B200.  The file name sorts last on purpose.
+
+* the persistent, flag-synchronised triangular solve (csrc/trsv.cu: trsv_persistent_kernel,
+  SPBLAS_B200_TRSV_PERSISTENT=1): same arithmetic per row as the level launches, so x must be
+  BIT-IDENTICAL to the reference's, in ONE launch, and the give-up flag must stay 0."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+import spblas_reference_b200 as sb
+from spblas_reference_b200 import generators as G
+from helpers import csr_on_device, dev
+from test_gpu_trsv import DIAG, UPLO, _solve, _tri_matrix
+
+pytestmark = [
+    pytest.mark.gpu,
+    pytest.mark.skipif(os.environ.get("SPBLAS_B200_RUN_UNVALIDATED") != "1",
+                       reason="never run on a GPU yet (SPBLAS_B200_RUN_UNVALIDATED=1 runs it)"),
+]
+
+
+@pytest.mark.parametrize("ctas", ["0", "1"])
+@pytest.mark.parametrize("kind", ["short", "mixed", "chain"])
+@pytest.mark.parametrize("types", [(np.float32, np.int32, np.int32), (np.float64, np.int32, np.int64),
+                                   (np.float32, np.int64, np.int64)])
+def test_trsv_persistent_bit_exact(cuda, oracle, monkeypatch, kind, types, ctas):
+    monkeypatch.setenv("SPBLAS_B200_TRSV_PERSISTENT", "1")
+    monkeypatch.setenv("SPBLAS_B200_TRSV_CTAS_PER_SM", ctas)     # 1: a small grid, many rounds per thread
+    vt, it, ot = types
+    rng = np.random.default_rng(zlib.crc32(f"ptrsv{kind}{vt.__name__}{ot.__name__}".encode()))
+    m = 40_000 if kind != "chain" else 3000                      # > one round of the 1-CTA-per-SM grid
+    v, rp, ci = _tri_matrix(rng, m, kind, vt, it, ot)
+    b = rng.standard_normal(m).astype(vt)
+    a = csr_on_device(v, rp, ci, (m, m))
+    for upper in (0, 1):
+        for unit in (0, 1):
+            info = sb.triangular_solve_inspect(a, UPLO[upper], DIAG[unit], dev(b),
+                                               torch.empty(m, dtype=dev(b).dtype, device="cuda"))
+            for kw in ({}, {"alpha_a": 0.5, "alpha_b": -2.0}):      # repeated solves: the epoch moves on
+                want = oracle.trsv(m, rp, ci, v, b, upper=upper, unit=unit, **kw)
+                got = _solve(a, upper, unit, b, m, info=info, **kw)
+                assert np.array_equal(got, want, equal_nan=True), (kind, upper, unit, kw)
+                assert info.last_launches == 1 and info.trsv_timeout == 0
+            assert np.array_equal(_solve(a, upper, unit, b, m, info=info, inplace=True),
+                                  oracle.trsv(m, rp, ci, v, b, upper=upper, unit=unit), equal_nan=True)
+            assert info.trsv_timeout == 0
+            info.close()
+
+
+def test_trsv_persistent_poisson_wavefront(cuda, oracle, monkeypatch):
+    """The stencil's anti-diagonal wavefront (1023 levels of <= 512 rows): every row waits on
+    rows one level up, many levels are in flight at once."""
+    monkeypatch.setenv("SPBLAS_B200_TRSV_PERSISTENT", "1")
+    g = 512
+    v, rp, ci, shape = G.poisson2d_csr(g, torch.float64, "cuda:0")
+    a = sb.csr_view(v, rp, ci, shape, int(ci.numel()))
+    m = shape[0]
+    b = np.random.default_rng(3).standard_normal(m)
+    want = None
+    for tri in (sb.lower_triangle, sb.upper_triangle):
+        x = torch.full((m,), float("nan"), dtype=torch.float64, device="cuda")
+        info = sb.triangular_solve_inspect(a, tri, sb.explicit_diagonal, dev(b), x)
+        assert info.trsv_levels == 2 * g - 1
+        for _ in range(3):
+            sb.triangular_solve(info, a, tri, sb.explicit_diagonal, dev(b), x)
+        torch.cuda.synchronize()
+        assert info.last_launches == 1 and info.trsv_timeout == 0
+        want = oracle.trsv(m, rp.cpu().numpy(), ci.cpu().numpy(), v.cpu().numpy(), b,
+                           upper=tri is sb.upper_triangle)
+        assert np.array_equal(x.cpu().numpy(), want)
+        info.close()
