@@ -194,7 +194,11 @@ def run_reference_arm(args):
         "data": "synthetic",
         "config": {"workload": f"C2 poisson2d {g}x{g} CSR SpMV fp64/int32, iterated y->x, "
                                "alpha=1/8 via scaled(); one full product per step",
-                   "rows": m, "nnz": nnz},
+                   "rows": m, "nnz": nnz,
+                   "sample_of": (f"the {args.gpus}-GPU arm's weak-scaled workload ({g * args.gpus}x{g} "
+                                 f"grid): one GPU's {g}x{g} block of rows per step — a rate "
+                                 "(GFLOP/s) of a serial code does not depend on how many blocks "
+                                 "it is given") if args.gpus > 1 else "the 1-GPU arm's full workload"},
         "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": 1, "kind": kind,
                          "sample": "the full product, every step (reference CPU multiply is "
                                    "serial: 1 thread)",
