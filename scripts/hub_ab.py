@@ -1,6 +1,7 @@
 """A/B of the warp-stream kernel (variant 2) and the hub-stream kernel (variant 3) on an
 R-MAT matrix: python scripts/hub_ab.py [scale] [fp32|fp64] [cap,cap,...].  One JSON line per
 run; cap 0 = the plain walk (variant 2), otherwise the hub table's size in columns."""
+# next measurement (round 2): python scripts/hub_ab.py 24 fp32 0,32768,32768g,40960g,49152g
 import json
 import os
 import sys
@@ -13,7 +14,8 @@ from spblas_reference_b200 import generators as G
 
 scale = int(sys.argv[1]) if len(sys.argv) > 1 else 22
 dtype = torch.float64 if len(sys.argv) > 2 and sys.argv[2] == "fp64" else torch.float32
-# "32768p": the walk also prefetches the next chunk's indices (SPBLAS_B200_HUB_PREFETCH=1)
+# "32768g": the gathers that go to memory bypass L1 (SPBLAS_B200_HUB_GATHER_CG=1).  (The "p"
+# runs in profiles/r01_hub_ab_rmat.jsonl were an index prefetch, since removed: no gain.)
 caps = sys.argv[3].split(",") if len(sys.argv) > 3 else ["0", "49152"]
 dev = torch.device("cuda:0")
 v, rp, ci, shape = G.rmat_csr(scale, 16, seed=24, dtype=dtype, device=dev)
@@ -23,9 +25,9 @@ a = sb.csr_view(v, rp, ci, shape, nnz)
 x = G.dense_uniform((n,), 5, dtype, dev)
 y_plain = None
 for spec in caps:
-    prefetch = spec.endswith("p")
-    cap = int(spec.rstrip("p"))
-    os.environ["SPBLAS_B200_HUB_PREFETCH"] = "1" if prefetch else "0"   # read at plan creation
+    cg = spec.endswith("g")
+    cap = int(spec.rstrip("g"))
+    os.environ["SPBLAS_B200_HUB_GATHER_CG"] = "1" if cg else "0"        # read at plan creation
     y = torch.empty(m, dtype=dtype, device=dev)
     info = sb.multiply_inspect(a, x, y)
     if cap > 0:
@@ -49,7 +51,7 @@ for spec in caps:
     ms = t0.elapsed_time(t1) / reps
     if cap == 0:
         y_plain = y
-    print(json.dumps({"scale": scale, "dtype": str(dtype), "cap": cap, "prefetch": prefetch, "variant": info.spmv_variant,
+    print(json.dumps({"scale": scale, "dtype": str(dtype), "cap": cap, "gather_cg": cg, "variant": info.spmv_variant,
                       "ms": round(ms, 4), "first_execute_ms": round(first_ms, 3), "nnz": nnz,
                       "hub_count": info.hub_count,
                       "hub_ref_share": round(info.hub_refs / max(nnz, 1), 4),

@@ -197,8 +197,8 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->ws_carveout = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_HUB"))
     p->hub_enable = std::atoi(v) != 0;
-  if (const char* v = std::getenv("SPBLAS_B200_HUB_PREFETCH"))
-    p->hub_prefetch = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SPBLAS_B200_HUB_GATHER_CG"))
+    p->hub_gather_cg = std::atoi(v) != 0;
   if (const char* v = std::getenv("SPBLAS_B200_HUB_COLS"))
     p->hub_cap_override = std::max<long long>(0, std::atoll(v));
   if (const char* v = std::getenv("SPBLAS_B200_HUB_MIN_COUNT"))

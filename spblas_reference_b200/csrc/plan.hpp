@@ -183,7 +183,7 @@ struct spblas_b200_plan {
   // that wants the hub variant (the table's size depends on the value width).
   int hub_state = 0;           // 0: not analysed for the current structure, 1: table built, -1: analysed, no hubs
   int hub_enable = 0;          // env SPBLAS_B200_HUB / spblas_b200_plan_set_hub: the automatic choice may pick the hub variant
-  int hub_prefetch = 0;        // env SPBLAS_B200_HUB_PREFETCH: the walk loads the next chunk's indices one step ahead
+  int hub_gather_cg = 0;       // env SPBLAS_B200_HUB_GATHER_CG: non-hub gathers bypass L1 (to be measured)
   int64_t hub_cap = 0;         // capacity (columns) the table was built for
   int64_t hub_cap_override = 0; // env SPBLAS_B200_HUB_COLS / set_hub (0: what shared memory holds)
   int64_t hub_min_count = 0;   // env SPBLAS_B200_HUB_MIN_COUNT / set_hub (0: 2 x SM count)

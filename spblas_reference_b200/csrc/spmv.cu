@@ -754,10 +754,11 @@ __device__ __forceinline__ T ld_hub(uint32_t hub, int slot) {
   }
 }
 
-// PF: the column indices of the NEXT chunk are loaded at the top of every step (8 more
-// registers for 4-byte indices), so that their trip to HBM overlaps this chunk's gathers
-// and row sums instead of opening the next step.
-template <typename T, typename I, typename O, bool HUB, int WARPS, bool PF = false>
+// CG: the gathers of x that do go to memory bypass L1 (ld.global.cg) — with a hit rate
+// under 1 % beside a large hub table, L1 only limits how many of them can be in flight.
+// (Tried and removed: loading the next chunk's indices one step ahead, +8 registers —
+// 1.034 -> 1.032 ms on R-MAT scale 24, profiles/r01_hub_ab_rmat.jsonl.)
+template <typename T, typename I, typename O, bool HUB, int WARPS, bool CG = false>
 __device__ __forceinline__ void
 ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
                 const T* __restrict__ values, const O* __restrict__ perm,
@@ -794,24 +795,8 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
     T carry = T(0);            // lane 0: that part's sum over the chunks already done
     int k = cur;
     int kb = 0;
-    [[maybe_unused]] Quad<I> pf[2];
-    [[maybe_unused]] bool pf_ok[2] = {false, false};
     do {
       const int kend = kb + kWsChunk < k_e ? kb + kWsChunk : k_e;
-      [[maybe_unused]] Quad<I> now[2];
-      [[maybe_unused]] bool now_ok[2] = {false, false};
-      if constexpr (PF) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          now[u] = pf[u];
-          now_ok[u] = pf_ok[u];
-          // a whole quad of the next chunk, inside the stream and inside the arrays
-          const int kn = kb + kWsChunk + 4 * (lane + 32 * u);
-          pf_ok[u] = kn < k_e && kn + 4 <= arr_end;
-          if (pf_ok[u])
-            pf[u] = ld_stream_quad(ci + kn);
-        }
-      }
       // ---- products of this chunk: two quads per lane -----------------------------
       T p[2][4];
 #pragma unroll
@@ -824,14 +809,7 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
           Quad<I> c;
           Quad<T> v;
           if (kk + 4 <= arr_end) {
-            if constexpr (PF) {
-              if (now_ok[u])
-                c = now[u];
-              else
-                c = ld_stream_quad(ci + kk);
-            } else {
-              c = ld_stream_quad(ci + kk);
-            }
+            c = ld_stream_quad(ci + kk);
             if (!has_perm) {
               v = ld_stream_quad(va + kk);
             } else {
@@ -854,7 +832,8 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if constexpr (HUB)
-              xv[j] = c.v[j] < I(0) ? ld_hub<T>(hub, int(~c.v[j])) : ld_ro(x + c.v[j]);
+              xv[j] = c.v[j] < I(0) ? ld_hub<T>(hub, int(~c.v[j]))
+                                    : (CG ? __ldcg(x + c.v[j]) : ld_ro(x + c.v[j]));
             else
               xv[j] = ld_ro(x + c.v[j]);
           }
@@ -998,7 +977,7 @@ spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ coli
 // C4 1.13 -> 1.03 ms with 32768 columns; larger tables lose (L1 shrinks).
 constexpr int kHubWarps = 32; // one CTA per SM
 
-template <typename T, typename O, bool PF>
+template <typename T, typename O, bool CG>
 __global__ void __launch_bounds__(kHubWarps * 32, 1)
 spmv_hub_stream_kernel(const O* __restrict__ rowptr, const int32_t* __restrict__ hub_colind,
                        const T* __restrict__ values, const O* __restrict__ perm,
@@ -1019,7 +998,7 @@ spmv_hub_stream_kernel(const O* __restrict__ rowptr, const int32_t* __restrict__
   const int warp = threadIdx.x >> 5;
   uint32_t hub_addr = smem_u32(hub);
   asm volatile("" : "+r"(hub_addr)); // one register, not a recomputation at every use
-  ws_walk_streams<T, int32_t, O, true, kHubWarps, PF>(
+  ws_walk_streams<T, int32_t, O, true, kHubWarps, CG>(
       rowptr, hub_colind, values, perm, x, y, alpha, starts, stream_first, num_streams, rows,
       nnz_end, carry_row, carry_val, sc, lane, warp, slabs + warp * kWsChunk, hub_addr);
 }
@@ -1338,8 +1317,8 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
         grid = p->num_sms;
       const size_t smem =
           (size_t(kHubWarps) * kWsChunk + size_t(p->hub_count)) * sizeof(T);
-      auto kern = p->hub_prefetch ? spmv_hub_stream_kernel<T, O, true>
-                                  : spmv_hub_stream_kernel<T, O, false>;
+      auto kern = p->hub_gather_cg ? spmv_hub_stream_kernel<T, O, true>
+                                   : spmv_hub_stream_kernel<T, O, false>;
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
       if (e != cudaSuccess)
         return cuda_fail(p, e, "cudaFuncSetAttribute(spmv_hub_stream_kernel)");

@@ -4,7 +4,9 @@ run on a B200.  The file name sorts last on purpose.
 
 * the persistent, flag-synchronised triangular solve (csrc/trsv.cu: trsv_persistent_kernel,
   SPBLAS_B200_TRSV_PERSISTENT=1): same arithmetic per row as the level launches, so x must be
-  BIT-IDENTICAL to the reference's, in ONE launch, and the give-up flag must stay 0."""
+  BIT-IDENTICAL to the reference's, in ONE launch, and the give-up flag must stay 0;
+* the hub-stream kernel with its memory gathers bypassing L1 (SPBLAS_B200_HUB_GATHER_CG=1):
+  the same arithmetic, so y must be bit-identical to the warp-stream kernel's."""
 import os
 import zlib
 
@@ -16,6 +18,7 @@ import spblas_reference_b200 as sb
 from spblas_reference_b200 import generators as G
 from helpers import csr_on_device, dev
 from test_gpu_trsv import DIAG, UPLO, _solve, _tri_matrix
+from test_gpu_zhub import _lens, _run, _skewed_csr
 
 pytestmark = [
     pytest.mark.gpu,
@@ -74,3 +77,20 @@ def test_trsv_persistent_poisson_wavefront(cuda, oracle, monkeypatch):
                            upper=tri is sb.upper_triangle)
         assert np.array_equal(x.cpu().numpy(), want)
         info.close()
+
+
+@pytest.mark.parametrize("kind", ["short", "hubrow", "long"])
+@pytest.mark.parametrize("vt", [np.float32, np.float64, np.int32])
+def test_hub_gathers_bypassing_l1(cuda, oracle, monkeypatch, kind, vt):
+    rng = np.random.default_rng(zlib.crc32(f"hubcg{kind}{vt.__name__}".encode()))
+    m, n = 5003, 2777
+    v, rp, ci, x = _skewed_csr(rng, m, n, _lens(rng, m, kind), vt)
+    a = csr_on_device(v, rp, ci, (m, n))
+    xd = dev(x)
+    y_ws, i_ws = _run(a, xd, m, 2)
+    monkeypatch.setenv("SPBLAS_B200_HUB_GATHER_CG", "1")          # read when the plan is created
+    y_hub, i_hub = _run(a, xd, m, 3, hub=(64, 3))
+    assert i_hub.spmv_variant == 3 and i_hub.hub_count == 64
+    assert torch.equal(y_ws, y_hub)
+    i_ws.close()
+    i_hub.close()
