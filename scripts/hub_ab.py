@@ -1,7 +1,7 @@
 """A/B of the warp-stream kernel (variant 2) and the hub-stream kernel (variant 3) on an
 R-MAT matrix: python scripts/hub_ab.py [scale] [fp32|fp64] [cap,cap,...].  One JSON line per
 run; cap 0 = the plain walk (variant 2), otherwise the hub table's size in columns."""
-# next measurement (round 2): python scripts/hub_ab.py 24 fp32 0,32768,32768g,40960g,49152g
+# next measurement (round 2): python scripts/hub_ab.py 24 fp32 0,0g,32768,32768g,40960g,49152g
 import json
 import os
 import sys
@@ -28,6 +28,7 @@ for spec in caps:
     cg = spec.endswith("g")
     cap = int(spec.rstrip("g"))
     os.environ["SPBLAS_B200_HUB_GATHER_CG"] = "1" if cg else "0"        # read at plan creation
+    os.environ["SPBLAS_B200_WS_GATHER_CG"] = "1" if (cg and cap == 0) else "0"   # "0g": plain walk
     y = torch.empty(m, dtype=dtype, device=dev)
     info = sb.multiply_inspect(a, x, y)
     if cap > 0:

@@ -193,6 +193,8 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     if (t >= 256 && t <= (1 << 20))
       p->ws_items_override = t;
   }
+  if (const char* v = std::getenv("SPBLAS_B200_WS_GATHER_CG"))
+    p->ws_gather_cg = std::atoi(v) != 0;
   if (const char* v = std::getenv("SPBLAS_B200_WS_CARVEOUT"))
     p->ws_carveout = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_HUB"))

@@ -172,6 +172,7 @@ struct spblas_b200_plan {
   int64_t ws_streams = -1;         // -1: table not built for the current structure
   int ws_items = 0;                // merge items per stream
   int ws_items_override = 0;       // env SPBLAS_B200_WS_ITEMS (tuning)
+  int ws_gather_cg = 0;            // env SPBLAS_B200_WS_GATHER_CG: gathers of x bypass L1 (experiment, unmeasured)
   int ws_carveout = -1;            // shared-memory carve-out in percent (env SPBLAS_B200_WS_CARVEOUT; -1 default)
   b200::DeviceBuffer ws_starts;    // int64 (row, nnz) pairs, ws_streams + 1 entries
   b200::DeviceBuffer ws_carry_row; // int64 per stream

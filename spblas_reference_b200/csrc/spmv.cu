@@ -835,7 +835,7 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
               xv[j] = c.v[j] < I(0) ? ld_hub<T>(hub, int(~c.v[j]))
                                     : (CG ? __ldcg(x + c.v[j]) : ld_ro(x + c.v[j]));
             else
-              xv[j] = ld_ro(x + c.v[j]);
+              xv[j] = CG ? __ldcg(x + c.v[j]) : ld_ro(x + c.v[j]);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -942,7 +942,7 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
   }
 }
 
-template <typename T, typename I, typename O>
+template <typename T, typename I, typename O, bool CG = false>
 __global__ void __launch_bounds__(kWsWarps * 32, ws_ctas_per_sm<T, I>())
 spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
                         const T* __restrict__ values, const O* __restrict__ perm,
@@ -955,7 +955,7 @@ spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ coli
   __shared__ __align__(16) T s_slab[kWsWarps][kWsChunk];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  ws_walk_streams<T, I, O, false, kWsWarps>(rowptr, colind, values, perm, x, y, alpha, starts,
+  ws_walk_streams<T, I, O, false, kWsWarps, CG>(rowptr, colind, values, perm, x, y, alpha, starts,
                                             stream_first, num_streams, rows, nnz_end,
                                             carry_row, carry_val, sc, lane, warp, s_slab[warp],
                                             0u);
@@ -1362,9 +1362,12 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
       carve = int((need * 100 + p->smem_per_sm - 1) / p->smem_per_sm);
       carve = carve > 100 ? 100 : carve;
     }
-    cudaFuncSetAttribute(spmv_warp_stream_kernel<T, I, O>,
-                         cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    spmv_warp_stream_kernel<T, I, O><<<unsigned(grid), kWsWarps * 32, 0, p->stream>>>(
+    // (SPBLAS_B200_WS_GATHER_CG=1: the gathers bypass L1 — an experiment on what bounds
+    // the misses in flight; not measured yet)
+    auto kern = p->ws_gather_cg ? spmv_warp_stream_kernel<T, I, O, true>
+                                : spmv_warp_stream_kernel<T, I, O, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    kern<<<unsigned(grid), kWsWarps * 32, 0, p->stream>>>(
         static_cast<const O*>(p->csr_rowptr), static_cast<const I*>(p->csr_colind),
         static_cast<const T*>(values), static_cast<const O*>(p->csr_perm),
         static_cast<const T*>(x), static_cast<T*>(y), a,

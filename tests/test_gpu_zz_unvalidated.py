@@ -94,3 +94,19 @@ def test_hub_gathers_bypassing_l1(cuda, oracle, monkeypatch, kind, vt):
     assert torch.equal(y_ws, y_hub)
     i_ws.close()
     i_hub.close()
+
+
+@pytest.mark.parametrize("vt", [np.float32, np.float64])
+def test_warp_stream_gathers_bypassing_l1(cuda, oracle, monkeypatch, vt):
+    """SPBLAS_B200_WS_GATHER_CG=1: the plain walk with ld.global.cg gathers — the same sums."""
+    rng = np.random.default_rng(77)
+    m, n = 5003, 2777
+    v, rp, ci, x = _skewed_csr(rng, m, n, _lens(rng, m, "hubrow"), vt)
+    a = csr_on_device(v, rp, ci, (m, n))
+    xd = dev(x)
+    y_ws, i_ws = _run(a, xd, m, 2)
+    monkeypatch.setenv("SPBLAS_B200_WS_GATHER_CG", "1")
+    y_cg, i_cg = _run(a, xd, m, 2)
+    assert i_cg.spmv_variant == 2 and torch.equal(y_ws, y_cg)
+    i_ws.close()
+    i_cg.close()
