@@ -276,7 +276,7 @@ def run_extra(args, sb, G, dev, peak, peak_src, sampler):
             extra[key] = {"error": repr(exc)}
     achieved = nbytes / (ms * 1e-3) / 1e9
     from bench import ncu_traffic
-    traffic = ncu_traffic(wl)
+    traffic = ncu_traffic("c4_plain_walk" if wl == "c4" and extra.get("spmv_variant") != 3 else wl)
     if wl.startswith("c3"):
         extra["spmm_variant"] = info.spmm_variant
     # same-box vendor comparator (the reference's NVIDIA backend is a cuSPARSE wrapper)
