@@ -183,7 +183,7 @@ SPBLAS_B200_API int spblas_b200_plan_cache_values(spblas_b200_plan* plan, int va
    set_hub(1, -1, -1) from multiply_inspect when the operand is wrapped in matrix_opt —
    the reference's marker for "the backend may keep optimised state for this matrix"
    (views/matrix_opt_impl.hpp:14-93).  Measured on R-MAT scale 24, fp32 (C4): 1.13 ms ->
-   1.03 ms; the analysis costs about 40 products, once.
+   1.03 ms; the analysis costs 10-50 products, once.
    int32 column indices only; plans inspected through multiply_inspect only (the no-info
    overloads never analyse).  Also read from the environment at plan creation:
    SPBLAS_B200_HUB, SPBLAS_B200_HUB_COLS, SPBLAS_B200_HUB_MIN_COUNT.  No reference
