@@ -362,3 +362,87 @@ def test_trsv_levels(oracle):
     # a diagonal matrix has one level; a bidiagonal one has m
     assert oracle.trsv_levels(4, [0, 1, 2, 3, 4], [0, 1, 2, 3]).max() == 0
     assert oracle.trsv_levels(4, [0, 1, 3, 5, 7], [0, 0, 1, 1, 2, 2, 3]).tolist() == [0, 1, 2, 3]
+
+
+def test_fuzz_restatement_against_the_real_reference(oracle):
+    """Property test (hypothesis): on arbitrary small structures — empty matrices, empty rows,
+    unsorted and duplicate columns, one-row / one-column shapes — the C restatement and the
+    real spblas::multiply agree bit for bit, for SpMV and SpMM, CSR and CSC, plain and scaled."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @st.composite
+    def case(draw):
+        m = draw(st.integers(0, 12))
+        n = draw(st.integers(1, 9))
+        lens = [draw(st.integers(0, 7)) for _ in range(m)]
+        seed = draw(st.integers(0, 2 ** 31 - 1))
+        k = draw(st.integers(1, 5))
+        vt = draw(st.sampled_from([np.float32, np.float64, np.int32]))
+        return m, n, lens, seed, k, vt
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(case())
+    def run(c):
+        m, n, lens, seed, k, vt = c
+        rng = np.random.default_rng(seed)
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        nnz = int(rp[-1])
+        ci = rng.integers(0, n, size=nnz).astype(np.int32)         # unsorted, duplicates legal
+        if vt == np.int32:
+            v = rng.integers(-9, 9, size=nnz).astype(vt)
+            x = rng.integers(-9, 9, size=n).astype(vt)
+            B = rng.integers(-9, 9, size=(n, k)).astype(vt)
+            xt = rng.integers(-9, 9, size=m).astype(vt)
+            aa = 3
+        else:
+            v = rng.standard_normal(nnz).astype(vt)
+            x = rng.standard_normal(n).astype(vt)
+            B = rng.standard_normal((n, k)).astype(vt)
+            xt = rng.standard_normal(m).astype(vt)
+            aa = 0.75
+        for kw in ({}, {"alpha_a": aa}):
+            assert np.array_equal(oracle.spmv("csr", (m, n), rp, ci, v, x, **kw),
+                                  oracle.spmv("csr", (m, n), rp, ci, v, x, impl="reference", **kw))
+            assert np.array_equal(oracle.spmm("csr", (m, n), rp, ci, v, B, **kw),
+                                  oracle.spmm("csr", (m, n), rp, ci, v, B, impl="reference", **kw))
+        # the same arrays read column-major: the n x m transpose
+        assert np.array_equal(oracle.spmv("csc", (n, m), rp, ci, v, xt),
+                              oracle.spmv("csc", (n, m), rp, ci, v, xt, impl="reference"))
+
+    run()
+
+
+def test_fuzz_transpose_and_trsv_against_the_real_reference(oracle):
+    """Property test (hypothesis): transpose (structure AND values) and triangular_solve (both
+    triangles, both diagonal modes, rows with or without a stored diagonal, duplicates) agree
+    bit for bit with the real reference on arbitrary small structures."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(1, 11), st.integers(1, 8), st.integers(0, 2 ** 31 - 1),
+           st.sampled_from([np.float32, np.float64]), st.integers(0, 6))
+    def run(m, n, seed, vt, maxlen):
+        rng = np.random.default_rng(seed)
+        lens = rng.integers(0, maxlen + 1, size=m)
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        nnz = int(rp[-1])
+        ci = rng.integers(0, n, size=nnz).astype(np.int32)
+        v = rng.standard_normal(nnz).astype(vt)
+        for a, b in zip(oracle.transpose((m, n), rp, ci, v),
+                        oracle.transpose((m, n), rp, ci, v, impl="reference")):
+            assert a.dtype == b.dtype and np.array_equal(a, b)
+        # a square matrix over the same rows for the solve
+        cs = rng.integers(0, m, size=nnz).astype(np.int32)
+        vs = (0.2 * rng.standard_normal(nnz)).astype(vt)
+        b = rng.standard_normal(m).astype(vt)
+        for upper in (0, 1):
+            for unit in (0, 1):
+                got = oracle.trsv(m, rp, cs, vs, b, upper=upper, unit=unit)
+                want = oracle.trsv(m, rp, cs, vs, b, upper=upper, unit=unit, impl="reference")
+                assert np.array_equal(got, want, equal_nan=True)
+
+    run()
