@@ -94,7 +94,8 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+        os.close(fd)
         self.proc = None
         self.gpu = gpu_index
 
