@@ -111,6 +111,10 @@ class ClockSampler:
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
             return out
         time.sleep(0.15)
         self.proc.terminate()
