@@ -420,24 +420,6 @@ def run_trsv(args, sb, G, dev, peak, peak_src, sampler):
     ms_direct = _time_loop(lambda i: sb.triangular_solve(info0, a, sb.lower_triangle,
                                                          sb.explicit_diagonal, b, x0), max(3, K // 4), 2)
     same_paths = bool(torch.equal(x, x0))
-    # the persistent flag-synchronised solve (one launch; opt-in until it is the faster one)
-    persistent = None
-    if os.environ.get("SPBLAS_B200_TRSV_PERSISTENT") is None:
-        try:
-            os.environ["SPBLAS_B200_TRSV_PERSISTENT"] = "1"
-            info1 = sb.triangular_solve_inspect(a, sb.lower_triangle, sb.explicit_diagonal, b, x)
-            x1 = torch.empty_like(x)
-            ms1 = _time_loop(lambda i: sb.triangular_solve(info1, a, sb.lower_triangle,
-                                                           sb.explicit_diagonal, b, x1),
-                             max(3, K // 4), 2)
-            persistent = {"ms_per_step": ms1, "launches_per_solve": info1.last_launches,
-                          "timeout_flag": info1.trsv_timeout,
-                          "bit_identical_to_headline": bool(torch.equal(x, x1))}
-            info1.close()
-        except Exception as exc:                   # a side number never costs the line
-            persistent = {"error": repr(exc)}
-        finally:
-            os.environ.pop("SPBLAS_B200_TRSV_PERSISTENT", None)
     used = (nnz + m) // 2                       # stored entries of the lower triangle incl. diagonal
     flops = 2.0 * used
     nbytes = nnz * 12 + (m + 1) * 4 + 3 * m * 8   # whole rows are read; b read, x read and written
@@ -465,7 +447,6 @@ def run_trsv(args, sb, G, dev, peak, peak_src, sampler):
                    "inspect_sweeps": info.trsv_sweeps,
                    "ms_per_step_level_by_level_launches": ms_direct,
                    "graph_and_direct_bit_identical": same_paths,
-                   "persistent_flag_synchronised_solve": persistent,
                    "us_per_level": ms * 1e3 / max(info.trsv_levels, 1)},
         "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak,
                      "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "traffic": None,

@@ -107,8 +107,8 @@ enum {
   SPBLAS_B200_Q_HUB_REFS = 21,      /* int64[1]: stored entries that reference a hub column         */
   SPBLAS_B200_Q_HUB_COLS = 22,      /* int32[hub_count]: the hub columns, ascending                 */
   SPBLAS_B200_Q_HUB_COLIND = 23,    /* int32[nnz]: the plan's re-encoded colind (hub number s -> ~s) */
-  SPBLAS_B200_Q_TRSV_TIMEOUT = 24   /* int64[1]: 1 if a row of a persistent triangular solve gave up
-                                       waiting for a dependency (the result is then invalid)       */
+  SPBLAS_B200_Q_SPMM_SLICES = 24    /* int64[1]: passes over A of the last SpMM (column slices of B
+                                       narrow enough to stay in L2; 1 = one pass)                 */
 };
 
 /* most destinations / peers of a fused exchange (one NVSwitch domain: 8 GPUs) */
@@ -253,11 +253,7 @@ SPBLAS_B200_API int spblas_b200_spmm_once(
        the reference's order, every one rounded separately: bit-identical results.
        alpha_a / alpha_b (HOST pointers, NULL = absent) are the factors of scaled(alpha, a)
        and scaled(alpha, b), applied per element as the reference's views do.  d_b may
-       alias d_x.  f32 and f64 values.
-     With SPBLAS_B200_TRSV_PERSISTENT=1 in the environment at plan creation the solve is ONE
-     launch instead: rows in level order, one thread per row, per-row ready flags (same
-     arithmetic, bit-identical x; a wait that never ends raises SPBLAS_B200_Q_TRSV_TIMEOUT
-     instead of hanging).  Not the default: written without GPU time left, to be measured. */
+       alias d_x.  f32 and f64 values. */
 SPBLAS_B200_API int spblas_b200_trsv_inspect(spblas_b200_plan* plan, int64_t m, int64_t nnz,
                                              const void* d_rowptr, const void* d_colind,
                                              int off_type, int idx_type, int upper,

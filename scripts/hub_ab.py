@@ -1,7 +1,6 @@
 """A/B of the warp-stream kernel (variant 2) and the hub-stream kernel (variant 3) on an
 R-MAT matrix: python scripts/hub_ab.py [scale] [fp32|fp64] [cap,cap,...].  One JSON line per
 run; cap 0 = the plain walk (variant 2), otherwise the hub table's size in columns."""
-# next measurement (round 2): python scripts/hub_ab.py 24 fp32 0,0g,32768,32768g,40960g,49152g
 import json
 import os
 import sys
@@ -14,8 +13,9 @@ from spblas_reference_b200 import generators as G
 
 scale = int(sys.argv[1]) if len(sys.argv) > 1 else 22
 dtype = torch.float64 if len(sys.argv) > 2 and sys.argv[2] == "fp64" else torch.float32
-# "32768g": the gathers that go to memory bypass L1 (SPBLAS_B200_HUB_GATHER_CG=1).  (The "p"
-# runs in profiles/r01_hub_ab_rmat.jsonl were an index prefetch, since removed: no gain.)
+# (The "g" runs in profiles/r02_hub_ab_l1_bypass.jsonl were L1-bypassing gathers, since made the
+# hub kernel's only mode and removed from the plain walk; the "p" runs in
+# profiles/r01_hub_ab_rmat.jsonl an index prefetch, since removed: no gain.)
 caps = sys.argv[3].split(",") if len(sys.argv) > 3 else ["0", "49152"]
 dev = torch.device("cuda:0")
 v, rp, ci, shape = G.rmat_csr(scale, 16, seed=24, dtype=dtype, device=dev)
@@ -25,10 +25,7 @@ a = sb.csr_view(v, rp, ci, shape, nnz)
 x = G.dense_uniform((n,), 5, dtype, dev)
 y_plain = None
 for spec in caps:
-    cg = spec.endswith("g")
-    cap = int(spec.rstrip("g"))
-    os.environ["SPBLAS_B200_HUB_GATHER_CG"] = "1" if cg else "0"        # read at plan creation
-    os.environ["SPBLAS_B200_WS_GATHER_CG"] = "1" if (cg and cap == 0) else "0"   # "0g": plain walk
+    cap = int(spec)
     y = torch.empty(m, dtype=dtype, device=dev)
     info = sb.multiply_inspect(a, x, y)
     if cap > 0:
@@ -52,7 +49,7 @@ for spec in caps:
     ms = t0.elapsed_time(t1) / reps
     if cap == 0:
         y_plain = y
-    print(json.dumps({"scale": scale, "dtype": str(dtype), "cap": cap, "gather_cg": cg, "variant": info.spmv_variant,
+    print(json.dumps({"scale": scale, "dtype": str(dtype), "cap": cap, "variant": info.spmv_variant,
                       "ms": round(ms, 4), "first_execute_ms": round(first_ms, 3), "nnz": nnz,
                       "hub_count": info.hub_count,
                       "hub_ref_share": round(info.hub_refs / max(nnz, 1), 4),

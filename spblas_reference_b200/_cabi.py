@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libspblas_b200.so")
+# SPBLAS_B200_LIB: another build of the same library (A/B measurements of one experiment)
+LIB_PATH = os.environ.get("SPBLAS_B200_LIB") or os.path.join(_PKG, "libspblas_b200.so")
 
 # ---- enums (include/spblas_b200.h) ------------------------------------------------
 SUCCESS, INVALID_ARGUMENT, SHAPE_MISMATCH, NOT_SUPPORTED = 0, 1, 2, 3
@@ -24,7 +25,7 @@ INSPECT_DEFAULT, INSPECT_LIGHT = 0, 1
  Q_SPMV_VARIANT, Q_LAST_LAUNCHES, Q_TOTAL_LAUNCHES, Q_CSR_ROWPTR, Q_CSR_COLIND,
  Q_CSR_PERM, Q_NUM_SEGMENTS, Q_SEGMENTS, Q_SPMM_VARIANT, Q_TILE_UNIFORM,
  Q_BARRIER_EPOCH, Q_BARRIER_TIMEOUT, Q_TRSV_LEVELS, Q_TRSV_SWEEPS,
- Q_HUB_COUNT, Q_HUB_REFS, Q_HUB_COLS, Q_HUB_COLIND, Q_TRSV_TIMEOUT) = range(25)
+ Q_HUB_COUNT, Q_HUB_REFS, Q_HUB_COLS, Q_HUB_COLIND, Q_SPMM_SLICES) = range(25)
 MAX_PEERS = 8
 HIST_BINS = 40
 

@@ -68,8 +68,7 @@ void release_all(spblas_b200_plan* p) {
                           &p->spmm_carry_row, &p->spmm_carry_val, &p->barrier_state,
                           &p->ws_starts, &p->ws_carry_row, &p->ws_carry_val, &p->own_values,
                           &p->trsv_level, &p->trsv_order, &p->trsv_tmp0, &p->trsv_tmp1,
-                          &p->trsv_level_ptr, &p->hub_cols, &p->hub_colind,
-                          &p->trsv_row_ready, &p->trsv_state};
+                          &p->trsv_level_ptr, &p->hub_cols, &p->hub_colind};
   for (DeviceBuffer* b : bufs)
     release(*b);
   release(p->hc_colmax);
@@ -193,24 +192,16 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     if (t >= 256 && t <= (1 << 20))
       p->ws_items_override = t;
   }
-  if (const char* v = std::getenv("SPBLAS_B200_WS_GATHER_CG"))
-    p->ws_gather_cg = std::atoi(v) != 0;
   if (const char* v = std::getenv("SPBLAS_B200_WS_CARVEOUT"))
     p->ws_carveout = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_HUB"))
     p->hub_enable = std::atoi(v) != 0;
-  if (const char* v = std::getenv("SPBLAS_B200_HUB_GATHER_CG"))
-    p->hub_gather_cg = std::atoi(v) != 0;
   if (const char* v = std::getenv("SPBLAS_B200_HUB_COLS"))
     p->hub_cap_override = std::max<long long>(0, std::atoll(v));
   if (const char* v = std::getenv("SPBLAS_B200_HUB_MIN_COUNT"))
     p->hub_min_count = std::max<long long>(0, std::atoll(v));
   if (const char* v = std::getenv("SPBLAS_B200_TRSV_INSPECT"))
     p->trsv_relax_inspect = std::string(v) == "relax";
-  if (const char* v = std::getenv("SPBLAS_B200_TRSV_PERSISTENT"))
-    p->trsv_persistent = std::atoi(v) != 0;
-  if (const char* v = std::getenv("SPBLAS_B200_TRSV_CTAS_PER_SM"))
-    p->trsv_persistent_ctas = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_TRSV_GRAPH"))
     p->trsv_use_graph = std::atoi(v) != 0;
   if (const char* v = std::getenv("SPBLAS_B200_HOST_CHUNKS"))
@@ -221,6 +212,8 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->spmm_ctas_per_sm = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_SPMM_L2FRAC"))
     p->spmm_l2_fraction = float(std::atof(v));
+  if (const char* v = std::getenv("SPBLAS_B200_SPMM_SLICE"))
+    p->spmm_slice_cols = std::atoll(v);
   *out = p;
   return SPBLAS_B200_SUCCESS;
 }
@@ -625,15 +618,6 @@ int spblas_b200_plan_query(spblas_b200_plan* p, int what, void* out,
     }
     return scalar(int64_t(st[1]));
   }
-  case SPBLAS_B200_Q_TRSV_TIMEOUT: {
-    unsigned int st = 0;
-    if (p->trsv_state.p) {
-      B200_CUDA_TRY(p, cudaMemcpyAsync(&st, p->trsv_state.p, sizeof(st), cudaMemcpyDeviceToHost,
-                                       p->stream));
-      B200_CUDA_TRY(p, cudaStreamSynchronize(p->stream));
-    }
-    return scalar(int64_t(st));
-  }
   case SPBLAS_B200_Q_TRSV_LEVELS:
     return scalar(p->trsv_ready ? p->trsv_levels : 0);
   case SPBLAS_B200_Q_TRSV_SWEEPS:
@@ -679,6 +663,8 @@ int spblas_b200_plan_query(spblas_b200_plan* p, int what, void* out,
     return scalar(p->spmv_variant);
   case SPBLAS_B200_Q_SPMM_VARIANT:
     return scalar(p->spmm_variant);
+  case SPBLAS_B200_Q_SPMM_SLICES:
+    return scalar(p->spmm_slices_last);
   case SPBLAS_B200_Q_CSR_ROWPTR:
     return device_array(p->csr_rowptr, size_t(p->csr_rows + 1) * so);
   case SPBLAS_B200_Q_CSR_COLIND:

@@ -129,13 +129,6 @@ struct spblas_b200_plan {
   cudaGraphExec_t trsv_graph[2] = {nullptr, nullptr};
   cudaStream_t trsv_capture_stream = nullptr;
   b200::DeviceBuffer trsv_params;        // operands of the current solve, read by the graph's kernels
-  // one persistent launch in level order with per-row ready flags (trsv_persistent_kernel):
-  // env SPBLAS_B200_TRSV_PERSISTENT=1; not the default until measured on a B200
-  bool trsv_persistent = false;
-  int trsv_persistent_ctas = 0;          // env SPBLAS_B200_TRSV_CTAS_PER_SM (0: what fits)
-  int trsv_epoch = 0;                    // solves so far: the value a row's flag takes when x_i is final
-  b200::DeviceBuffer trsv_row_ready;        // int32 per row: epoch of the solve that last wrote x_i
-  b200::DeviceBuffer trsv_state;         // uint32: 1 if a row gave up waiting for a dependency
 
   // ---- merge-path partition --------------------------------------------------
   int tile_items = b200::kSpmvTileItems;
@@ -167,12 +160,15 @@ struct spblas_b200_plan {
   int spmm_forced = -1;              // env SPBLAS_B200_SPMM_VARIANT: 0 group kernel, 1 stream kernel
   int spmm_ctas_per_sm = 0;          // env SPBLAS_B200_SPMM_CTAS_PER_SM (0 = what fits)
   float spmm_l2_fraction = -1.f;     // env SPBLAS_B200_SPMM_L2FRAC: share of B kept evict_last (<0: auto)
+  // Column slicing (spmm.cu, run_spmm): when B is larger than L2 the product runs as
+  // several passes over A, each against a column slice of B narrow enough to stay in L2.
+  int64_t spmm_slice_cols = 0;       // env SPBLAS_B200_SPMM_SLICE: columns per pass (0: model decides, -1: never)
+  int64_t spmm_slices_last = 1;      // passes of the last product (SPBLAS_B200_Q_SPMM_SLICES)
 
   // ---- SpMV warp streams (spmv_warp_stream_kernel) ----------------------------------
   int64_t ws_streams = -1;         // -1: table not built for the current structure
   int ws_items = 0;                // merge items per stream
   int ws_items_override = 0;       // env SPBLAS_B200_WS_ITEMS (tuning)
-  int ws_gather_cg = 0;            // env SPBLAS_B200_WS_GATHER_CG: gathers of x bypass L1 (experiment, unmeasured)
   int ws_carveout = -1;            // shared-memory carve-out in percent (env SPBLAS_B200_WS_CARVEOUT; -1 default)
   b200::DeviceBuffer ws_starts;    // int64 (row, nnz) pairs, ws_streams + 1 entries
   b200::DeviceBuffer ws_carry_row; // int64 per stream
@@ -184,7 +180,6 @@ struct spblas_b200_plan {
   // that wants the hub variant (the table's size depends on the value width).
   int hub_state = 0;           // 0: not analysed for the current structure, 1: table built, -1: analysed, no hubs
   int hub_enable = 0;          // env SPBLAS_B200_HUB / spblas_b200_plan_set_hub: the automatic choice may pick the hub variant
-  int hub_gather_cg = 0;       // env SPBLAS_B200_HUB_GATHER_CG: non-hub gathers bypass L1 (to be measured)
   int64_t hub_cap = 0;         // capacity (columns) the table was built for
   int64_t hub_cap_override = 0; // env SPBLAS_B200_HUB_COLS / set_hub (0: what shared memory holds)
   int64_t hub_min_count = 0;   // env SPBLAS_B200_HUB_MIN_COUNT / set_hub (0: 2 x SM count)

@@ -754,11 +754,37 @@ __device__ __forceinline__ T ld_hub(uint32_t hub, int slot) {
   }
 }
 
-// CG: the gathers of x that do go to memory bypass L1 (ld.global.cg) — with a hit rate
-// under 1 % beside a large hub table, L1 only limits how many of them can be in flight.
+// CG: the gathers of x that do go to memory bypass L1 (ld.global.cg).  Measured on R-MAT scale
+// 24 (profiles/r02_hub_ab_l1_bypass.jsonl): beside the hub table, where L1 is small and its hit
+// rate under 1 %, bypassing wins (fp32 1.032 -> 1.021 ms, fp64 1.439 -> 1.360 ms) — the hub
+// kernel always does it; in the plain walk, whose L1 is large, it loses badly (1.127 ->
+// 1.691 ms) — the plain walk never does.
 // (Tried and removed: loading the next chunk's indices one step ahead, +8 registers —
 // 1.034 -> 1.032 ms on R-MAT scale 24, profiles/r01_hub_ab_rmat.jsonl.)
-template <typename T, typename I, typename O, bool HUB, int WARPS, bool CG = false>
+// L2 policy of the walk (build-time switches, measured in profiles/r02_l2_policy.txt):
+// the streams of A (colind, values, permutation, row ends) are read once per product and
+// carry an evict_first hint, so that on a matrix whose A is many times L2 (C5: 3.2 GB per
+// GPU against 126 MB) they do not push out the columns of x that are gathered again and
+// again; the gathers of x themselves may carry evict_last.
+#ifndef B200_WS_A_EF
+#define B200_WS_A_EF 0
+#endif
+#ifndef B200_WS_X_EL
+#define B200_WS_X_EL 0
+#endif
+constexpr bool kWsStreamEF = B200_WS_A_EF != 0;
+
+template <bool CG, typename T>
+__device__ __forceinline__ T ws_gather(const T* p) {
+  if constexpr (CG)
+    return __ldcg(p);
+  else if constexpr (B200_WS_X_EL != 0)
+    return ld_ro_el(p);
+  else
+    return ld_ro(p);
+}
+
+template <typename T, typename I, typename O, bool HUB, int WARPS>
 __device__ __forceinline__ void
 ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
                 const T* __restrict__ values, const O* __restrict__ perm,
@@ -809,11 +835,11 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
           Quad<I> c;
           Quad<T> v;
           if (kk + 4 <= arr_end) {
-            c = ld_stream_quad(ci + kk);
+            c = ld_stream_quad_p<kWsStreamEF>(ci + kk);
             if (!has_perm) {
-              v = ld_stream_quad(va + kk);
+              v = ld_stream_quad_p<kWsStreamEF>(va + kk);
             } else {
-              const Quad<O> pi = ld_stream_quad(perm + base + kk);
+              const Quad<O> pi = ld_stream_quad_p<kWsStreamEF>(perm + base + kk);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 v.v[j] = ld_ro(values + pi.v[j]);
@@ -822,10 +848,10 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const bool in = kk + j < arr_end;
-              c.v[j] = in ? ld_stream(ci + kk + j) : I(0);
+              c.v[j] = in ? ld_stream_p<kWsStreamEF>(ci + kk + j) : I(0);
               v.v[j] = !in ? T(0)
                            : (has_perm ? ld_ro(values + perm[base + kk + j])
-                                       : ld_stream(va + kk + j));
+                                       : ld_stream_p<kWsStreamEF>(va + kk + j));
             }
           }
           T xv[4];
@@ -833,9 +859,9 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
           for (int j = 0; j < 4; ++j) {
             if constexpr (HUB)
               xv[j] = c.v[j] < I(0) ? ld_hub<T>(hub, int(~c.v[j]))
-                                    : (CG ? __ldcg(x + c.v[j]) : ld_ro(x + c.v[j]));
+                                    : ws_gather<HUB>(x + c.v[j]);
             else
-              xv[j] = CG ? __ldcg(x + c.v[j]) : ld_ro(x + c.v[j]);
+              xv[j] = ws_gather<HUB>(x + c.v[j]);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -845,7 +871,7 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
       // ---- rows that end inside the chunk -------------------------------------------
       int re = 0x7fffffff;
       if (lane < rows_left)
-        re = int(int64_t(ld_stream(rowptr + row + 1 + lane)) - base);
+        re = int(int64_t(ld_stream_p<kWsStreamEF>(rowptr + row + 1 + lane)) - base);
       unsigned mask = __ballot_sync(0xffffffffu, re <= kend);
       if (mask == 0u) {
         // the chunk lies inside one row: no shared memory, straight to the shuffle tree
@@ -914,7 +940,7 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
             break;
           re = 0x7fffffff;
           if (lane < rows_left)
-            re = int(int64_t(ld_stream(rowptr + row + 1 + lane)) - base);
+            re = int(int64_t(ld_stream_p<kWsStreamEF>(rowptr + row + 1 + lane)) - base);
           mask = __ballot_sync(0xffffffffu, re <= kend);
           if (mask == 0u)
             break;
@@ -942,7 +968,7 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
   }
 }
 
-template <typename T, typename I, typename O, bool CG = false>
+template <typename T, typename I, typename O>
 __global__ void __launch_bounds__(kWsWarps * 32, ws_ctas_per_sm<T, I>())
 spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
                         const T* __restrict__ values, const O* __restrict__ perm,
@@ -955,7 +981,7 @@ spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ coli
   __shared__ __align__(16) T s_slab[kWsWarps][kWsChunk];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  ws_walk_streams<T, I, O, false, kWsWarps, CG>(rowptr, colind, values, perm, x, y, alpha, starts,
+  ws_walk_streams<T, I, O, false, kWsWarps>(rowptr, colind, values, perm, x, y, alpha, starts,
                                             stream_first, num_streams, rows, nnz_end,
                                             carry_row, carry_val, sc, lane, warp, s_slab[warp],
                                             0u);
@@ -977,7 +1003,7 @@ spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ coli
 // C4 1.13 -> 1.03 ms with 32768 columns; larger tables lose (L1 shrinks).
 constexpr int kHubWarps = 32; // one CTA per SM
 
-template <typename T, typename O, bool CG>
+template <typename T, typename O>
 __global__ void __launch_bounds__(kHubWarps * 32, 1)
 spmv_hub_stream_kernel(const O* __restrict__ rowptr, const int32_t* __restrict__ hub_colind,
                        const T* __restrict__ values, const O* __restrict__ perm,
@@ -998,7 +1024,7 @@ spmv_hub_stream_kernel(const O* __restrict__ rowptr, const int32_t* __restrict__
   const int warp = threadIdx.x >> 5;
   uint32_t hub_addr = smem_u32(hub);
   asm volatile("" : "+r"(hub_addr)); // one register, not a recomputation at every use
-  ws_walk_streams<T, int32_t, O, true, kHubWarps, CG>(
+  ws_walk_streams<T, int32_t, O, true, kHubWarps>(
       rowptr, hub_colind, values, perm, x, y, alpha, starts, stream_first, num_streams, rows,
       nnz_end, carry_row, carry_val, sc, lane, warp, slabs + warp * kWsChunk, hub_addr);
 }
@@ -1317,8 +1343,7 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
         grid = p->num_sms;
       const size_t smem =
           (size_t(kHubWarps) * kWsChunk + size_t(p->hub_count)) * sizeof(T);
-      auto kern = p->hub_gather_cg ? spmv_hub_stream_kernel<T, O, true>
-                                   : spmv_hub_stream_kernel<T, O, false>;
+      auto kern = spmv_hub_stream_kernel<T, O>;
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
       if (e != cudaSuccess)
         return cuda_fail(p, e, "cudaFuncSetAttribute(spmv_hub_stream_kernel)");
@@ -1362,10 +1387,7 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
       carve = int((need * 100 + p->smem_per_sm - 1) / p->smem_per_sm);
       carve = carve > 100 ? 100 : carve;
     }
-    // (SPBLAS_B200_WS_GATHER_CG=1: the gathers bypass L1 — an experiment on what bounds
-    // the misses in flight; not measured yet)
-    auto kern = p->ws_gather_cg ? spmv_warp_stream_kernel<T, I, O, true>
-                                : spmv_warp_stream_kernel<T, I, O, false>;
+    auto kern = spmv_warp_stream_kernel<T, I, O>;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     kern<<<unsigned(grid), kWsWarps * 32, 0, p->stream>>>(
         static_cast<const O*>(p->csr_rowptr), static_cast<const I*>(p->csr_colind),

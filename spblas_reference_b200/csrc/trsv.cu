@@ -220,85 +220,11 @@ trsv_level_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
                     alpha_b, b, x);
 }
 
-// ---- one persistent launch, rows in (level, row) order, per-row ready flags -------------
-// Thread g takes positions g, g + G, g + 2G, ... of the level-sorted row list.  A row's
-// dependencies sit at EARLIER positions, i.e. with a thread that has already finished them
-// or is working on them right now (the whole grid is resident: it is sized from the
-// occupancy query), so waiting always ends.  Each thread is a small state machine inside ONE
-// loop — poll the flag of the next dependency, or fold the next entry into the dot product,
-// or finish the row, publish it and move on — so a lane never parks at a reconvergence
-// point while it holds a result another lane of its warp is waiting for.  Entries are folded
-// in storage order with separately rounded operations: the same arithmetic as trsv_row.
-// x_i is stored, then ready[i] = epoch with release semantics; a consumer acquires the flag
-// and reads x_k from L2 (ld.cg: an L1 line may predate the store).  A wait that exceeds
-// kTrsvSpinLimit polls raises state[0] and goes on with whatever x_k holds: a wrong
-// result that the host can detect (SPBLAS_B200_Q_TRSV_TIMEOUT), never a hang.
-constexpr unsigned kTrsvSpinLimit = 1u << 22;
-
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-template <typename T, typename I, typename O>
-__global__ void __launch_bounds__(256)
-trsv_persistent_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
-                       const T* __restrict__ values, const int* __restrict__ order,
-                       const int64_t m, const int upper, const int unit, const int has_aa,
-                       const T alpha_a, const int has_ab, const T alpha_b, const T* b, T* x,
-                       int* ready, const int epoch, unsigned int* state) {
-  const int64_t G = int64_t(gridDim.x) * blockDim.x;
-  int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= m)
-    return;
-  int64_t i = order[t];
-  O p = rowptr[i], end = rowptr[i + 1];
-  T dot = T(0), diag = T(0);
-  unsigned spins = 0;
-  for (;;) {
-    if (p < end) {
-      const int64_t k = int64_t(colind[p]);
-      const bool dep = upper ? k > i : k < i;
-      if (dep && ld_acquire_gpu(ready + k) != epoch) {
-        if (++spins < kTrsvSpinLimit) {
-          if (spins > 4)
-            __nanosleep(spins > 64 ? 256 : 64); // waiting rows must not crowd the L2 ports
-          continue;
-        }
-        atomicExch(state, 1u);
-      }
-      T a_v = values[p];
-      if (has_aa)
-        a_v = mul_rn(alpha_a, a_v);
-      if (dep)
-        dot = add_rn(dot, mul_rn(a_v, __ldcg(x + k)));
-      else if (k == i)
-        diag = a_v; // the last stored diagonal entry wins, as in the reference
-      ++p;
-      spins = 0;
-    } else {
-      T b_i = b[i];
-      if (has_ab)
-        b_i = mul_rn(alpha_b, b_i);
-      const T num = sub_rn(b_i, dot);
-      x[i] = unit ? num : div_rn(num, diag);
-      st_release_gpu(ready + i, epoch);
-      t += G;
-      if (t >= m)
-        break;
-      i = order[t];
-      p = rowptr[i];
-      end = rowptr[i + 1];
-      dot = T(0);
-      diag = T(0);
-    }
-  }
-}
+// (A persistent variant — ONE launch, rows in level order, per-row ready flags polled with
+// ld.acquire — was written, validated bit-identical on a B200 and measured: 281 ms per solve
+// on the 4096^2 stencil against 43.7 ms for the graph replay below, because every one of the
+// 8191 wavefronts crosses L2 with an acquire/release pair per row.  It was removed;
+// profiles/r02_bench_trsv_persistent_vs_graph.json keeps the measurement.)
 
 } // namespace
 
@@ -344,16 +270,6 @@ int trsv_inspect_typed(spblas_b200_plan* p, int64_t m, const void* d_rowptr,
   release_trsv_graphs(p); // they replay the previous structure's levels
   if (m == 0)
     return SPBLAS_B200_SUCCESS;
-  if (p->trsv_persistent) {
-    // per-row ready flags of the persistent solve: no row of this structure is final yet
-    if (int rc = reserve(p, p->trsv_row_ready, size_t(m) * sizeof(int)))
-      return rc;
-    if (int rc = reserve(p, p->trsv_state, 4 * sizeof(unsigned int)))
-      return rc;
-    B200_CUDA_TRY(p, cudaMemsetAsync(p->trsv_row_ready.p, 0, size_t(m) * sizeof(int), s));
-    B200_CUDA_TRY(p, cudaMemsetAsync(p->trsv_state.p, 0, 4 * sizeof(unsigned int), s));
-    p->trsv_epoch = 0;
-  }
 
   B200_CUDA_TRY(p, cudaMemsetAsync(level, 0, size_t(m) * sizeof(int), s));
   B200_CUDA_TRY(p, cudaMemsetAsync(stats, 0, 16 * sizeof(unsigned long long), s));
@@ -465,35 +381,6 @@ int trsv_solve_typed(spblas_b200_plan* p, const void* alpha_a, const void* alpha
   // overhead: the level launches are captured ONCE into a CUDA graph whose kernels read
   // the operands of the call from a small parameter block, and every solve replays it.
   const int slot = sizeof(T) == 8 ? 1 : 0;
-  if (p->trsv_persistent && p->trsv_m > 0) {
-    auto kern = trsv_persistent_kernel<T, I, O>;
-    int per_sm = 0;
-    B200_CUDA_TRY(p, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
-    if (per_sm < 1)
-      return fail(p, SPBLAS_B200_CUDA_ERROR, "trsv_persistent_kernel does not fit an SM");
-    if (p->trsv_persistent_ctas > 0 && p->trsv_persistent_ctas < per_sm)
-      per_sm = p->trsv_persistent_ctas;
-    // every CTA must be resident: waiting rows spin on rows of other CTAs
-    const int64_t grid =
-        std::min<int64_t>((p->trsv_m + 255) / 256, int64_t(per_sm) * p->num_sms);
-    if (p->trsv_epoch == 0x7fffffff) { // (one solve per microsecond for 35 minutes)
-      B200_CUDA_TRY(p, cudaMemsetAsync(p->trsv_row_ready.p, 0, size_t(p->trsv_m) * sizeof(int),
-                                       p->stream));
-      p->trsv_epoch = 0;
-    }
-    const int epoch = ++p->trsv_epoch;
-    kern<<<unsigned(grid), 256, 0, p->stream>>>(
-        static_cast<const O*>(p->trsv_rowptr), static_cast<const I*>(p->trsv_colind),
-        static_cast<const T*>(values), order, p->trsv_m, p->trsv_upper, p->trsv_unit,
-        alpha_a != nullptr, aa, alpha_b != nullptr, ab, static_cast<const T*>(b),
-        static_cast<T*>(x), static_cast<int*>(p->trsv_row_ready.p), epoch,
-        static_cast<unsigned int*>(p->trsv_state.p));
-    if (int rc = check(p, "trsv_persistent_kernel"))
-      return rc;
-    p->last_launches = 1;
-    p->total_launches += 1;
-    return SPBLAS_B200_SUCCESS;
-  }
   if (p->trsv_use_graph && p->trsv_levels >= 16) {
     if (int rc = reserve(p, p->trsv_params, sizeof(TrsvParams)))
       return rc;

@@ -186,6 +186,43 @@ def rmat_csr(scale: int, edge_factor: int, seed: int, dtype=torch.float32, devic
     return values, rowptr.to(off_dtype), colind, (nrows, n)
 
 
+def rmat_csr_blocked(scale: int, edge_factor: int, seed: int, deg: torch.Tensor,
+                     dtype=torch.float32, device="cpu", off_dtype=torch.int32,
+                     row_begin: int = 0, row_end: Optional[int] = None,
+                     max_block_nnz: int = 1 << 29, chunk_edges: int = 1 << 26):
+    """rmat_csr(...) of rows [row_begin, row_end) assembled from consecutive row sub-blocks of
+    at most ~max_block_nnz entries each (cut with the row degrees `deg` of the whole graph,
+    rmat_degrees): the same matrix, entry for entry, with the sort's temporaries bounded by
+    the sub-block instead of the block — scale 27 on ONE GPU is 2^31 entries, and sorting
+    them at once would need > 100 GB of temporaries.  Every sub-block scans all edges."""
+    n = 1 << scale
+    row_end = n if row_end is None else row_end
+    rp_all = torch.zeros(row_end - row_begin + 1, dtype=torch.int64, device=deg.device)
+    torch.cumsum(deg[row_begin:row_end], 0, out=rp_all[1:])
+    nnz = int(rp_all[-1])
+    pieces = max(1, -(-nnz // max_block_nnz))
+    if pieces == 1:
+        return rmat_csr(scale, edge_factor, seed, dtype, device, off_dtype, chunk_edges,
+                        row_begin, row_end)
+    targets = torch.tensor([(p * nnz) // pieces for p in range(1, pieces)], dtype=torch.int64,
+                           device=rp_all.device)
+    cuts = [0] + torch.searchsorted(rp_all, targets).tolist() + [row_end - row_begin]
+    vals, cols = [], []
+    for p in range(pieces):
+        a, b = row_begin + cuts[p], row_begin + max(cuts[p + 1], cuts[p])
+        if b <= a:
+            continue
+        v, _, c, _ = rmat_csr(scale, edge_factor, seed, dtype, device, torch.int64, chunk_edges, a, b)
+        vals.append(v)
+        cols.append(c)
+    values = torch.cat(vals) if vals else torch.empty(0, dtype=dtype, device=device)
+    del vals
+    colind = torch.cat(cols) if cols else torch.empty(0, dtype=torch.int32, device=device)
+    del cols
+    assert int(values.numel()) == nnz
+    return values, rp_all.to(off_dtype).to(device), colind, (row_end - row_begin, n)
+
+
 def to_csc(values, rowptr, colind, shape):
     """Column-major image of a CSR matrix (for CSC tests): stable sort by column, so a
     column's entries are in ascending row order."""

@@ -116,7 +116,7 @@ class operation_info_t:
     @property
     def trsv_sweeps(self): return self._query_scalar(_cabi.Q_TRSV_SWEEPS)
     @property
-    def trsv_timeout(self): return self._query_scalar(_cabi.Q_TRSV_TIMEOUT)
+    def spmm_slices(self): return self._query_scalar(_cabi.Q_SPMM_SLICES)
 
     @property
     def barrier_epoch(self): return self._query_scalar(_cabi.Q_BARRIER_EPOCH)

@@ -275,3 +275,39 @@ def test_hub_rmat_reduced(cuda, oracle, monkeypatch):
     assert_rows_within_bound(y_hub.cpu().numpy(), y_ref, rph, y_ref.astype(np.float64), "hub R-MAT 18")
     i_ws.close()
     i_hub.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_fuzz_spmv_kernels_on_arbitrary_small_structures(cuda, oracle, variant):
+    """Property test (hypothesis): every SpMV kernel on arbitrary small structures — no rows,
+    empty rows, one very long row, duplicates, a row block with a non-zero base — integer
+    scalars, so the answer is exact whatever the order of the sums."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(0, 300), st.integers(1, 200), st.integers(0, 2 ** 31 - 1),
+           st.sampled_from([0, 3, 9, 40]), st.integers(0, 700))
+    def run(m, n, seed, maxlen, long_row):
+        rng = np.random.default_rng(seed)
+        lens = rng.integers(0, maxlen + 1, size=m)
+        if m and long_row:
+            lens[rng.integers(0, m)] = long_row
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        nnz = int(rp[-1])
+        ci = rng.integers(0, n, size=nnz).astype(np.int32)
+        v = rng.integers(-9, 10, size=nnz).astype(np.int32)
+        x = rng.integers(-9, 10, size=n).astype(np.int32)
+        a = csr_on_device(v, rp, ci, (m, n))
+        xd = dev(x)
+        y, info = _run(a, xd, m, variant, hub=(16, 1) if variant == 3 else None, alpha=2)
+        assert np.array_equal(y.cpu().numpy(), oracle.spmv("csr", (m, n), rp, ci, v, x, alpha_a=2))
+        info.close()
+        if m >= 4:                                   # rows [r0, r1) with the global base
+            r0, r1 = m // 4, m - m // 4
+            blk = sb.csr_view(a.values, a.rowptr[r0:r1 + 1], a.colind, (r1 - r0, n),
+                              int(rp[r1] - rp[r0]))
+            yb, ib = _run(blk, xd, r1 - r0, variant, hub=(16, 1) if variant == 3 else None)
+            assert np.array_equal(yb.cpu().numpy(), oracle.spmv("csr", (m, n), rp, ci, v, x)[r0:r1])
+            ib.close()
+
+    run()
