@@ -14,6 +14,13 @@ At N>1 the run is WEAK-scaled: every rank owns one 4096 x 4096 grid's worth of r
 inspect phase found necessary (spblas_reference_b200/sharded.py).  value = GFLOP/s over all
 ranks, time = max over ranks (CUDA events).
 
+The same JSON line carries, under "configs", the other BASELINE.json configs measured in the
+same run (bench_configs.py): C1, C3 (k = 32, 128) and C4 at N=1, and C5 — R-MAT scale 27, SpMV
+and SpMM — STRONG-scaled over the N ranks at every N; each block has its own roofline,
+cpu_baseline, e2e and parity.  `--configs none` prints the headline alone, `--configs c1,c4`
+a selection.  Every result that is timed is also checked: "parity" compares the device result
+with the reference's CPU multiply under the north-star bound.
+
 `--impl reference` times the reference's own CPU multiply on the host (oracle/_ref when it
 was built from /root/reference, else the oracle port) on the same workload.
 
@@ -49,6 +56,10 @@ def parse():
                     help="C5 R-MAT scale (default 24 + log2(N): 16.7M rows per GPU; c5mm: "
                          "22 + log2(N))")
     ap.add_argument("--grid", type=int, default=4096, help="C2 grid edge (per GPU)")
+    ap.add_argument("--configs", default="all",
+                    help="blocks beside the headline: all | none | comma list of c1,c3k32,c3k128,c4,c5 "
+                         "(c5 includes its SpMM half; at N>1 only c5 applies)")
+    ap.add_argument("--c5-scale", type=int, default=27, help="R-MAT scale of the c5 block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -94,27 +105,29 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
-        os.close(fd)
+        self.path = None                       # created by start(): only the rank that samples has a file
         self.proc = None
         self.gpu = gpu_index
 
     def start(self):
+        fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            with os.fdopen(fd, "w") as out:    # the child keeps its own copy of the descriptor
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                     "--format=csv,noheader,nounits", "-lms", "100"],
+                    stdout=out, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
-            try:
-                os.unlink(self.path)
-            except OSError:
-                pass
+            if self.path:
+                try:
+                    os.unlink(self.path)
+                except OSError:
+                    pass
             return out
         time.sleep(0.15)
         self.proc.terminate()
@@ -179,7 +192,9 @@ def run_reference_arm(args):
     v, rp, ci, shape = host_matrix_c2(g, g, 0, g * g)
     m, n = shape
     nnz = len(ci)
-    x = np.ones(n, dtype=np.float64)
+    import torch
+    from spblas_reference_b200 import generators as G
+    x = G.dense_uniform((n,), 1, torch.float64, "cpu").numpy()      # the b200 arm's x0
     from oracle import oracle as O
     O.build()
     impl, kind = ("reference", "reference") if O.have_ref() else ("oracle", "port")
@@ -301,7 +316,9 @@ def main():
     a_scaled = sb.scaled(0.125, a)
     cmin, cmax = int(ci.min()), int(ci.max())
 
-    x0 = torch.ones(n, dtype=torch.float64, device=dev)
+    # x0 = U[0,1) (splitmix64, seed 1: SURVEY 8d's variant).  With x0 = 1 the iterate is 0 on
+    # every interior row from the second step on, and the timed loop would multiply zeros.
+    x0 = G.dense_uniform((n,), 1, torch.float64, dev)
     info = sb.multiply_inspect(a, x0, torch.empty(m_loc, dtype=torch.float64, device=dev))
     t_ins0 = time.perf_counter()
     sb.multiply_inspect(info, a, x0, torch.empty(m_loc, dtype=torch.float64, device=dev))
@@ -313,7 +330,6 @@ def main():
                      torch.float64, dev, info=info,
                      fused=None if os.environ.get("SPBLAS_B200_FUSED", "1") != "0" else False)
     op.set_x(x0)
-    del x0
 
     # ---- warm-up, then the timed region ---------------------------------------------------
     for _ in range(W):
@@ -345,8 +361,12 @@ def main():
     # nvidia-smi samples every 100 ms and the timed region is ~10 ms: keep the SAME loop
     # running (untimed) until the sampler has seen at least half a second of this load
     # (a step count derived from the all-reduced step time: every rank runs the same
-    # number of steps, as the exchange requires)
-    for _ in range(min(20000, int(600.0 / max(step_ms, 1e-3)))):
+    # number of steps, as the exchange requires).  The iterate decays like (1/8 A)^k: it is
+    # re-seeded every 64 steps so that the loop never multiplies denormals or zeros.
+    extra_steps = min(20000, int(600.0 / max(step_ms, 1e-3)))
+    for i in range(extra_steps):
+        if i % 64 == 0:
+            op.set_x(x0)
         op.step()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -360,13 +380,50 @@ def main():
     bytes_launch = spmv_bytes(nnz_loc, m_loc, x_touched, 8, 4, 4)
     achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
 
+    # ---- parity of what was timed: three more iterations of the (fused) y -> x loop from x0,
+    # then (1) every value this rank received is bit for bit the value its owner computed,
+    # (2) this rank's rows of the next product against the reference's CPU multiply fed with
+    # the same x (per iteration, not compounded).  The CPU product is also the cpu_baseline.
+    from bench_configs import check_spmv
+    op.set_x(x0)
+    del x0
+    for _ in range(3):
+        op.step()
+    x_in = op.x_current.clone()
+    replica_ok = True
+    if world > 1:
+        gathered = [torch.empty(m_loc, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, x_in[r0:r1].contiguous())
+        for peer, b0, e0_ in op.plan.recvs:
+            pb = blocks[peer][0]
+            replica_ok = replica_ok and bool(torch.equal(gathered[peer][b0 - pb:e0_ - pb], x_in[b0:e0_]))
+        del gathered
+    y_blk = op.step().clone()
+    torch.cuda.synchronize()
+    barrier_timeout = int(max_over_ranks(float(info.barrier_timeout))) if op.fused else 0
+    cpu, parity = None, None
+    if not args.no_cpu_baseline:
+        cpu, parity = check_spmv(rp, ci, v, x_in, 0.125, y_blk, (0, m_loc), n,
+                                 f"the full {g}x{g} product of rank {rank}", reps=3)
+        parity["max_err_over_tol"] = max_over_ranks(parity["max_err_over_tol"])
+        parity["rows_checked"] = int(sum_over_ranks(parity["rows_checked"]))
+        ok = parity["pass"] and replica_ok and barrier_timeout == 0
+        parity["pass"] = bool(max_over_ranks(0.0 if ok else 1.0) == 0.0)
+        parity["halo_bit_identical_to_owner"] = bool(max_over_ranks(0.0 if replica_ok else 1.0) == 0.0)
+        parity["after_iterations"] = 3
+        parity["what"] = ("after 3 iterations of the timed y->x loop: every received halo value == "
+                          "its owner's (bit for bit), and every rank's rows of the next product "
+                          "against the reference's CPU multiply on the same x")
+        if not (rank == 0 and world == 1):
+            cpu = None                                   # cpu_baseline: rank 0 at N=1 only
+
     if op.fused:                        # the plan goes back to plain products
         info.set_scatter(())
         info.set_barrier((), ())
     # ---- end to end through the public API with HOST buffers --------------------------------
     e2e = None
     if not args.no_e2e:
-        x_host = torch.ones(n, dtype=torch.float64).pin_memory()
+        x_host = x_in.cpu().pin_memory()
         y_host = torch.empty(m_loc, dtype=torch.float64).pin_memory()
         x_dev = torch.empty(n, dtype=torch.float64, device=dev)
         y_dev = torch.empty(m_loc, dtype=torch.float64, device=dev)
@@ -397,48 +454,39 @@ def main():
         serial_ms = time_e2e(e2e_step_serial)
         y_serial = y_host.clone()
         e2e_ms = time_e2e(e2e_step)
-        assert torch.equal(y_serial, y_host), "host-buffer execute differs from the device execute"
+        same = bool(torch.equal(y_serial, y_host)) and bool(torch.equal(y_host, y_blk.cpu()))
         e2e = {"value": flops_step / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
-               "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(m_loc * 8),
+               "h2d_bytes_per_step": int(n * 8) * world, "d2h_bytes_per_step": int(m_loc * 8) * world,
                "ms_per_step": e2e_ms, "steps": ke,
                "what": "multiply_execute_host: pinned host x -> device, SpMV kernels, y -> pinned "
                        "host, pipelined over 16 chunks of tiles inside one C-ABI call "
                        "(spblas_b200_spmv_host); A and the inspected plan stay resident "
-                       "(operator reuse, as in the y->x loop)",
+                       "(operator reuse, as in the y->x loop); every rank moves its own x and y",
                "serial_ms_per_step": serial_ms,
                "serial_what": "the same three steps issued one after the other (copy, "
-                              "multiply_execute, copy)"}
-        # sanity: the result is the known answer A*1/8 (interior rows 0)
-        assert torch.isfinite(y_host).all()
-
-    # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        vh, rph, cih = v.cpu().numpy(), rp.cpu().numpy(), ci.cpu().numpy()
-        xh = np.ones(n, dtype=np.float64)
-        reps = 5
-        sec, kind = cpu_reference_spmv_seconds(vh, rph, cih, shape, xh, reps, 0.125)
-        cpu = {"value": 2.0 * nnz_loc / sec / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": kind,
-               "sample": f"the full {g}x{g} product, best of {reps} (reference CPU multiply is "
-                         "serial: 1 thread)",
-               "seconds": sec, "host_cores_available": os.cpu_count()}
+                              "multiply_execute, copy)",
+               "bit_identical_to_device_path": same}
+        if parity is not None and not same:
+            parity["pass"] = False
+        del x_dev, y_dev, x_host, y_host, y_serial
 
     # ---- same-box vendor comparator: cuSPARSE as the reference's NVIDIA backend calls it ----
     cusparse = None
     if rank == 0 and world == 1:
         from bench_extra import cusparse_compare
-        xc = torch.ones(n, dtype=torch.float64, device=dev)
         yc = torch.empty(m_loc, dtype=torch.float64, device=dev)
-        cusparse = cusparse_compare("spmv", [(m_loc, n, rp, ci, v, xc, yc)], K, 0.125)
+        cusparse = cusparse_compare("spmv", [(m_loc, n, rp, ci, v, x_in, yc)], K, 0.125)
         if cusparse and "unavailable" not in cusparse:
             yo = torch.empty_like(yc)
-            sb.multiply_execute(info, a_scaled, xc, yo)
+            sb.multiply_execute(info, a_scaled, x_in, yo)
             torch.cuda.synchronize()
             cusparse["max_abs_diff_vs_ours"] = (yo - yc).abs().max().item()
             best = min(vv for kk, vv in cusparse.items() if kk.startswith("CUSPARSE_"))
             cusparse["ours_over_best_cusparse"] = best / kern_ms
-        del xc, yc
+            del yo
+        del yc
 
+    line = None
     if rank == 0:
         line = {
             "metric": "CSR SpMV GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world,
@@ -448,10 +496,10 @@ def main():
                 "workload": f"C2 poisson2d {g}x{g} per GPU ({gi}x{g} global) CSR SpMV fp64/int32, "
                             "iterated y->x, alpha=1/8 via scaled(); one full product per step",
                 "rows_per_gpu": m_loc, "nnz_per_gpu": nnz_loc, "parallelism": f"rowblock{world}",
+                "x0": "U[0,1), splitmix64 seed 1",
                 "exchange": op.plan.mode, "halo_elems_per_step": op.plan.recv_elems,
-                "exchange_impl": ("fused: peer stores from the SpMV kernels + flag barrier in the "
-                                  "fix-up kernel (no collective call)") if op.fused else
-                                 ("nccl" if world > 1 else "none"),
+                "exchange_impl": op.exchange_impl if world > 1 else "none",
+                "exchange_calibration": getattr(op, "calibration", None),
                 "l2_policy": "inputs larger than L2 (1.34 GB per product), no flush",
                 "inspect_ms": inspect_ms,
             },
@@ -468,8 +516,49 @@ def main():
             "gpu_launches": launches,
             "e2e": e2e,
             "cpu_baseline": cpu,
+            "parity": parity,
             "cusparse": cusparse,
         }
+
+    # ---- the other configs, in the same line -------------------------------------------------
+    del op, x_in, y_blk, a, a_scaled, v, rp, ci
+    info.close()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    wanted = {"all": ["c1", "c3k32", "c3k128", "c4", "c5"], "none": []}.get(
+        args.configs, [t for t in args.configs.split(",") if t])
+    if world > 1:
+        wanted = [t for t in wanted if t == "c5"]        # the single-GPU configs are N=1 blocks
+    configs, errors = {}, {}
+    if wanted:
+        import bench_configs as BC
+        ctx = {"sb": sb, "G": G, "dev": dev, "K": K, "W": W, "peak": peak, "peak_src": peak_src,
+               "traffic": ncu_traffic, "world": world, "rank": rank, "barrier": barrier,
+               "max": max_over_ranks, "sum": sum_over_ranks}
+        runners = {"c1": lambda: {"c1": BC.config_c1(ctx)},
+                   "c3k32": lambda: {"c3k32": BC.config_c3(ctx, 32)},
+                   "c3k128": lambda: {"c3k128": BC.config_c3(ctx, 128)},
+                   "c4": lambda: {"c4": BC.config_c4(ctx)},
+                   "c5": lambda: BC.config_c5(ctx, args.c5_scale)}
+        for name in wanted:
+            t0 = time.perf_counter()
+            try:
+                blocks_out = runners[name]()
+                for key, blk in blocks_out.items():
+                    blk["wall_s"] = time.perf_counter() - t0
+                    configs[key] = blk
+            except Exception as exc:               # a side block never costs the headline
+                if world > 1:
+                    raise                          # (ranks must not diverge inside collectives)
+                errors[name] = repr(exc)
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+    if rank == 0:
+        line["configs"] = configs
+        if errors:
+            line["config_errors"] = errors
+        line["parity_all_pass"] = bool((parity or {}).get("pass", False) and
+                                       all(b.get("parity", {}).get("pass", False) for b in configs.values()))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

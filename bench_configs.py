@@ -275,11 +275,10 @@ def config_c3(ctx, k):
     blk = {"workload": f"C3 CSR SpMM fp32 2M x 2M, 16 nnz/row, row-major B k={k}", "nnz": nnz,
            "ms": ms, "gflops": flops / ms / 1e6, "gbs": nbytes / ms / 1e6,
            "l2_policy": "inputs larger than L2",
-           "spmm_variant": info.spmm_variant, "passes_over_A": info.spmm_slices,
+           "spmm_variant": info.spmm_variant,
            "gather_model_bytes": nnz * 8 + (m + 1) * 4 + nnz * k * 4 + m * k * 4,
            "roofline": roofline(nbytes, ms, ctx["peak"], ctx["peak_src"], ctx["traffic"](f"c3k{k}"),
-                                "spmm_row_kernel (one launch per column slice)"
-                                if info.spmm_variant < 1000 else "spmm_ring_kernel"),
+                                "spmm_row_kernel" if info.spmm_variant < 1000 else "spmm_ring_kernel"),
            "cpu_baseline": cpu, "e2e": e2e, "parity": parity}
     info.close()
     return blk
@@ -457,10 +456,7 @@ def config_c5(ctx, scale=27, with_spmm=True):
           "generate_s": gen_s, "inspect_ms": inspect_ms, "max_row_len": info.max_row_len,
           "spmv_variant": info.spmv_variant, "gpu_launches": launches,
           "exchange": {"mode": op.plan.mode,
-                       "impl": ("fused: rows stored into the peers' x replicas by the SpMV kernels"
-                                + (" (one NVLS multimem.st per row)" if getattr(op, "multicast", False) else
-                                   " (peer stores over NVLink)") + " + flag barrier in the fix-up kernel")
-                       if op.fused else ("nccl broadcasts (allgatherv)" if world > 1 else "none"),
+                       "impl": op.exchange_impl, "calibration": op.calibration,
                        "bytes_received_per_gpu_per_step": exchange_bytes if world > 1 else 0,
                        "fused_error": op.fused_error, "barrier_timeout_flag": timeout_flag,
                        "ms_above_kernels": step_ms - kern_ms},
@@ -516,7 +512,7 @@ def config_c5(ctx, scale=27, with_spmm=True):
                     f"{world} nnz-balanced row block(s), B replicated, single product (no exchange)",
         "scaling": "strong", "n_gpus": world, "nnz": total_nnz, "ms": mm_ms, "steps": Km,
         "gflops": mm_flops / mm_ms / 1e6, "spmm_variant": info_mm.spmm_variant,
-        "passes_over_A": info_mm.spmm_slices, "num_segments": info_mm.num_segments,
+        "num_segments": info_mm.num_segments,
         "exchange": {"mode": "none", "bytes_received_per_gpu_per_step": 0},
         "roofline": roofline(mm_bytes, mm_ms, ctx["peak"], ctx["peak_src"],
                              ctx["traffic"](f"c5mm_n{world}"), "spmm (see spmm_variant)"),

@@ -107,8 +107,6 @@ enum {
   SPBLAS_B200_Q_HUB_REFS = 21,      /* int64[1]: stored entries that reference a hub column         */
   SPBLAS_B200_Q_HUB_COLS = 22,      /* int32[hub_count]: the hub columns, ascending                 */
   SPBLAS_B200_Q_HUB_COLIND = 23,    /* int32[nnz]: the plan's re-encoded colind (hub number s -> ~s) */
-  SPBLAS_B200_Q_SPMM_SLICES = 24    /* int64[1]: passes over A of the last SpMM (column slices of B
-                                       narrow enough to stay in L2; 1 = one pass)                 */
 };
 
 /* most destinations / peers of a fused exchange (one NVSwitch domain: 8 GPUs) */
@@ -301,7 +299,12 @@ SPBLAS_B200_API int spblas_b200_transpose(spblas_b200_plan* plan, int val_type,
      among the ranks: d_remote_slots[q] is this rank's slot in peer q's flag
      array (peer-mapped), d_local_slots[q] the slot peer q writes here; flags
      are uint64 step numbers, zero-initialised by the caller.  Every rank must
-     issue the same sequence of executes.  n_peers = 0 switches it off.
+     issue the same sequence of executes.  n_peers = 0 switches it off.  A rank that
+     waits longer than SPBLAS_B200_BARRIER_TIMEOUT_MS (environment at plan creation,
+     default 30000) for a peer gives up instead of hanging the GPU: that step's x is
+     incomplete, so the NEXT execute on the plan returns SPBLAS_B200_CUDA_ERROR (the flag
+     lives in host-mapped memory: no synchronisation is needed to see it) and
+     SPBLAS_B200_Q_BARRIER_TIMEOUT reports 1 from then on.
    Both are properties of the plan (operation_info_t state): multiply /
    multiply_execute keep the reference's signature. */
 SPBLAS_B200_API int spblas_b200_plan_set_scatter(spblas_b200_plan* plan, int n_dst,

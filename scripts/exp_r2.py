@@ -1,7 +1,6 @@
 """Round-2 A/B measurements (one JSON line per run; run on a B200 under gpurun):
 
   python scripts/exp_r2.py spmv  <workload> [reps]    workload: c1 | c4 | c5s24 | c5shard (scale 27, 1/8 of the rows)
-  python scripts/exp_r2.py spmm  <k> <slice,slice,..>  C3 matrix, slice = columns per pass (-1: never, 0: model)
   python scripts/exp_r2.py libs  <workload> lib,lib,.. the spmv run once per build of the library
                                                        (SPBLAS_B200_LIB; "base" = the shipped one)
 
@@ -106,37 +105,10 @@ def run_spmv(wl, reps):
                       "checksum": float(y.double().sum().item())}), flush=True)
 
 
-def run_spmm(k, slices, reps=20):
-    import torch
-    import spblas_reference_b200 as sb
-    from spblas_reference_b200 import generators as G
-    dev = torch.device("cuda:0")
-    m = n = 2_000_000
-    v, rp, ci, shape = G.uniform_random_csr(m, n, 16, seed=3, dtype=torch.float32, device=dev)
-    a = sb.csr_view(v, rp, ci, shape, int(ci.numel()))
-    B = G.dense_uniform((n, k), 4, torch.float32, dev)
-    ref = None
-    for sl in slices:
-        os.environ["SPBLAS_B200_SPMM_SLICE"] = str(sl)       # read at plan creation
-        C = torch.empty((m, k), device=dev)
-        info = sb.multiply_inspect(a, B, C)
-        ms = timed(lambda i: sb.multiply_execute(info, a, B, C), reps)
-        if ref is None:
-            ref = C
-        print(json.dumps({"exp": "spmm", "k": k, "slice": sl, "passes": info.spmm_slices,
-                          "variant": info.spmm_variant, "ms": round(ms, 4),
-                          "gflops": round(2.0 * a.nnz * k / ms / 1e6, 1),
-                          "max_abs_diff_vs_first": (C - ref).abs().max().item(),
-                          "bit_identical_to_first": bool(torch.equal(C, ref))}), flush=True)
-        info.close()
-
-
 if __name__ == "__main__":
     mode = sys.argv[1]
     if mode == "spmv":
         run_spmv(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 30)
-    elif mode == "spmm":
-        run_spmm(int(sys.argv[2]), [int(t) for t in sys.argv[3].split(",")])
     elif mode == "libs":
         for lib in sys.argv[3].split(","):
             env = dict(os.environ)

@@ -12,7 +12,14 @@ keys = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'sm__inst_executed_pipe_lsu.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts.sum',
-        'sm__cycles_elapsed.avg']
+        'sm__cycles_elapsed.avg',
+        # the gather path: requests and sectors between L1 and L2
+        'l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__m_xbar2l1tex_read_sectors.sum', 'lts__t_sectors_srcunit_tex_op_read.sum',
+        'lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum', 'lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
+        'lts__t_sectors_op_read.sum', 'lts__t_sectors_op_write.sum',
+        'dram__sectors_read.sum', 'dram__sectors_write.sum']
 keys += [h for h in hdr if h.startswith('smsp__average_warps_issue_stalled') and h.endswith('per_issue_active.ratio')]
 for k in keys:
     if k in hdr:

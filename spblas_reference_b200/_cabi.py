@@ -25,7 +25,7 @@ INSPECT_DEFAULT, INSPECT_LIGHT = 0, 1
  Q_SPMV_VARIANT, Q_LAST_LAUNCHES, Q_TOTAL_LAUNCHES, Q_CSR_ROWPTR, Q_CSR_COLIND,
  Q_CSR_PERM, Q_NUM_SEGMENTS, Q_SEGMENTS, Q_SPMM_VARIANT, Q_TILE_UNIFORM,
  Q_BARRIER_EPOCH, Q_BARRIER_TIMEOUT, Q_TRSV_LEVELS, Q_TRSV_SWEEPS,
- Q_HUB_COUNT, Q_HUB_REFS, Q_HUB_COLS, Q_HUB_COLIND, Q_SPMM_SLICES) = range(25)
+ Q_HUB_COUNT, Q_HUB_REFS, Q_HUB_COLS, Q_HUB_COLIND) = range(24)
 MAX_PEERS = 8
 HIST_BINS = 40
 

@@ -72,6 +72,9 @@ void release_all(spblas_b200_plan* p) {
   for (DeviceBuffer* b : bufs)
     release(*b);
   release(p->hc_colmax);
+  if (p->barrier_gave_up_h)
+    cudaFreeHost(p->barrier_gave_up_h);
+  p->barrier_gave_up_h = p->barrier_gave_up_d = nullptr;
   release_host_exec(p);
   release_trsv_graphs(p);
   release(p->trsv_params);
@@ -204,6 +207,11 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->trsv_relax_inspect = std::string(v) == "relax";
   if (const char* v = std::getenv("SPBLAS_B200_TRSV_GRAPH"))
     p->trsv_use_graph = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SPBLAS_B200_BARRIER_TIMEOUT_MS")) {
+    const long long t = std::atoll(v);
+    if (t > 0)
+      p->barrier_timeout_ms = (unsigned long long)t;
+  }
   if (const char* v = std::getenv("SPBLAS_B200_HOST_CHUNKS"))
     p->host_chunks_override = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_SPMM_VARIANT"))
@@ -212,8 +220,6 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->spmm_ctas_per_sm = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_SPMM_L2FRAC"))
     p->spmm_l2_fraction = float(std::atof(v));
-  if (const char* v = std::getenv("SPBLAS_B200_SPMM_SLICE"))
-    p->spmm_slice_cols = std::atoll(v);
   *out = p;
   return SPBLAS_B200_SUCCESS;
 }
@@ -279,6 +285,15 @@ int spblas_b200_plan_set_barrier(spblas_b200_plan* p, int n_peers,
     if (int rc = reserve(p, p->barrier_state, 2 * sizeof(unsigned int)))
       return rc;
     B200_CUDA_TRY(p, cudaMemsetAsync(p->barrier_state.p, 0, 2 * sizeof(unsigned int), p->stream));
+  }
+  if (!p->barrier_gave_up_h) {
+    void* h = nullptr;
+    B200_CUDA_TRY(p, cudaHostAlloc(&h, sizeof(unsigned int), cudaHostAllocMapped));
+    p->barrier_gave_up_h = static_cast<unsigned int*>(h);
+    *p->barrier_gave_up_h = 0u;
+    void* d = nullptr;
+    B200_CUDA_TRY(p, cudaHostGetDevicePointer(&d, h, 0));
+    p->barrier_gave_up_d = static_cast<unsigned int*>(d);
   }
   p->barrier.n = n_peers;
   return SPBLAS_B200_SUCCESS;
@@ -610,13 +625,12 @@ int spblas_b200_plan_query(spblas_b200_plan* p, int what, void* out,
   case SPBLAS_B200_Q_BARRIER_EPOCH:
     return scalar(int64_t(p->barrier_epoch));
   case SPBLAS_B200_Q_BARRIER_TIMEOUT: {
-    unsigned int st[2] = {0, 0};
-    if (p->barrier_state.p) {
-      B200_CUDA_TRY(p, cudaMemcpyAsync(st, p->barrier_state.p, sizeof(st),
-                                       cudaMemcpyDeviceToHost, p->stream));
+    unsigned int st = 0;
+    if (p->barrier_gave_up_h) {
       B200_CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+      st = *static_cast<volatile unsigned int*>(p->barrier_gave_up_h);
     }
-    return scalar(int64_t(st[1]));
+    return scalar(int64_t(st != 0 || p->barrier_gave_up_seen));
   }
   case SPBLAS_B200_Q_TRSV_LEVELS:
     return scalar(p->trsv_ready ? p->trsv_levels : 0);
@@ -663,8 +677,6 @@ int spblas_b200_plan_query(spblas_b200_plan* p, int what, void* out,
     return scalar(p->spmv_variant);
   case SPBLAS_B200_Q_SPMM_VARIANT:
     return scalar(p->spmm_variant);
-  case SPBLAS_B200_Q_SPMM_SLICES:
-    return scalar(p->spmm_slices_last);
   case SPBLAS_B200_Q_CSR_ROWPTR:
     return device_array(p->csr_rowptr, size_t(p->csr_rows + 1) * so);
   case SPBLAS_B200_Q_CSR_COLIND:

@@ -160,10 +160,6 @@ struct spblas_b200_plan {
   int spmm_forced = -1;              // env SPBLAS_B200_SPMM_VARIANT: 0 group kernel, 1 stream kernel
   int spmm_ctas_per_sm = 0;          // env SPBLAS_B200_SPMM_CTAS_PER_SM (0 = what fits)
   float spmm_l2_fraction = -1.f;     // env SPBLAS_B200_SPMM_L2FRAC: share of B kept evict_last (<0: auto)
-  // Column slicing (spmm.cu, run_spmm): when B is larger than L2 the product runs as
-  // several passes over A, each against a column slice of B narrow enough to stay in L2.
-  int64_t spmm_slice_cols = 0;       // env SPBLAS_B200_SPMM_SLICE: columns per pass (0: model decides, -1: never)
-  int64_t spmm_slices_last = 1;      // passes of the last product (SPBLAS_B200_Q_SPMM_SLICES)
 
   // ---- SpMV warp streams (spmv_warp_stream_kernel) ----------------------------------
   int64_t ws_streams = -1;         // -1: table not built for the current structure
@@ -201,7 +197,13 @@ struct spblas_b200_plan {
   b200::ScatterSpec scatter;
   b200::BarrierSpec barrier;
   unsigned long long barrier_epoch = 0; // steps signalled so far
-  b200::DeviceBuffer barrier_state;     // uint32 block counter, uint32 timeout flag
+  b200::DeviceBuffer barrier_state;     // uint32 block counter
+  // "a wait gave up" flag in host-mapped memory: the kernel sets it, the next execute reads it
+  // without a synchronisation and fails (a timeout must never be silent)
+  unsigned int* barrier_gave_up_h = nullptr;
+  unsigned int* barrier_gave_up_d = nullptr;
+  bool barrier_gave_up_seen = false;           // sticky copy for SPBLAS_B200_Q_BARRIER_TIMEOUT
+  unsigned long long barrier_timeout_ms = 30000; // env SPBLAS_B200_BARRIER_TIMEOUT_MS
 
   // ---- host-buffer execute (spblas_b200_spmv_host, host_exec.cu) -----------------
   // The tiles cut into `host_chunks` consecutive chunks; chunk c covers tiles

@@ -77,9 +77,8 @@ load_chunk(const I* __restrict__ colind, const T* __restrict__ values,
     c[sl] = I(0);
     v[sl] = T(0);
     if (idx < ke) {
-      // streamed once per pass: out of L2 first, the gathered slice of B stays
-      c[sl] = ld_stream_ef(colind + idx);
-      v[sl] = perm == nullptr ? ld_stream_ef(values + idx) : ld_ro(values + perm[idx]);
+      c[sl] = ld_stream(colind + idx);
+      v[sl] = perm == nullptr ? ld_stream(values + idx) : ld_ro(values + perm[idx]);
     }
   }
 }
@@ -842,10 +841,6 @@ int spmm_pass(spblas_b200_plan* p, const void* alpha, const void* values,
       p->spmm_variant = 100 * V + 2;
       return launch_spmm<T, I, O, V, 2>(p, a, values, B, ldb, C, ldc, k);
     }
-    if (nv <= 4) {
-      p->spmm_variant = 100 * V + 4;
-      return launch_spmm<T, I, O, V, 4>(p, a, values, B, ldb, C, ldc, k);
-    }
     if (nv <= 8) {
       p->spmm_variant = 100 * V + 8;
       return launch_spmm<T, I, O, V, 8>(p, a, values, B, ldb, C, ldc, k);
@@ -865,93 +860,16 @@ int spmm_pass(spblas_b200_plan* p, const void* alpha, const void* values,
   return launch_spmm<T, I, O, 1, 32>(p, a, values, B, ldb, C, ldc, k);
 }
 
-// ---- column slicing --------------------------------------------------------------------
-// Every stored entry of A gathers one row of B.  When B does not fit in L2 most of those
-// gathers go to DRAM (C3, k = 128: 16.6 GB moved for 2.3 GB of operands, ncu), and no
-// tiling of A creates reuse on a matrix with uniformly random columns: a row of B is used
-// nnz/n times in total, by rows that are anywhere.  What does shrink the gathered
-// footprint is the width: a slice of w columns of B is n * w * sizeof(T) bytes, and the
-// same random rows then hit L2.  So the product runs as ceil(k / w) passes over A, pass j
-// producing columns [j*w, (j+1)*w) of C from the same columns of B — the passes are
-// separate launches on the plan's stream, one slice is live in L2 at a time, A (streamed
-// with evict_first) is re-read once per pass, every element of C is still written exactly
-// once, by one thread, with the same operations in the same order: the result is
-// bit-identical to the single pass.  The width comes from a two-term model, DRAM bytes
-// against L2 requests (a gather is one request per 128-byte line per SM cycle):
-//   t(s) = max(bytes(s) / HBM, s * nnz * lines(w) / requests per second) + s * launch.
-template <typename T>
-int64_t spmm_slice_width(const spblas_b200_plan* p, int64_t k, bool vec) {
-  constexpr int64_t V = 16 / int64_t(sizeof(T));
-  if (!vec || p->spmm_slice_cols < 0 || k <= 2 * V)
-    return k;
-  if (p->spmm_slice_cols > 0) {
-    int64_t w = p->spmm_slice_cols / V * V;
-    w = w < V ? V : w;
-    return w < k ? w : k;
-  }
-  const double sT = double(sizeof(T));
-  const double l2 = 0.6 * double(p->l2_bytes); // what the gathered slice keeps beside the streams
-  const double n = double(p->csr_cols), m = double(p->csr_rows), nnz = double(p->nnz);
-  if (n * double(k) * sT <= l2 || nnz <= 0)
-    return k;
-  // The model assumes every row of B is equally likely.  The row-length histogram says when
-  // that is false: on a power-law matrix (R-MAT) the popular rows of B stay in L2 whatever the
-  // width, re-reading A buys nothing, and the narrow row kernel serialises the hub rows
-  // (measured: R-MAT scale 22, fp64, k = 32 in 8 passes — 93.7 ms per product,
-  // profiles/r02_bench_c5mm_s22_sliced_row_kernel_pathology.json).
-  const double mean_len = nnz / (m > 0 ? m : 1);
-  if (!p->have_hist || double(p->max_row_len) > (8.0 * mean_len > 64.0 ? 8.0 * mean_len : 64.0))
-    return k;
-  const double a_bytes = nnz * (sT + double(type_size_idx(p->idx_type))) +
-                         (m + 1) * double(type_size_idx(p->off_type));
-  const double c_bytes = m * double(k) * sT;
-  const double hbm = 6.0e12, req = double(p->num_sms) * 1.9e9 * 0.85, launch = 4e-6;
-  double best_t = 1e30;
-  int64_t best_w = k;
-  for (int64_t s = 1; s <= 64; ++s) {
-    int64_t w = ((k + s - 1) / s + V - 1) / V * V; // ceil(k / s) rounded up to whole vectors
-    if (w * int64_t(sizeof(T)) < 32)               // a gather moves 32-byte sectors
-      break;
-    const int64_t passes = (k + w - 1) / w;
-    if (passes != s)
-      continue;
-    const double seg = double(w) * sT;
-    const double footprint = n * seg;
-    const double miss = footprint <= l2 ? 0.0 : 1.0 - l2 / footprint;
-    const double used = (nnz < n ? nnz : n) * seg; // rows of the slice touched at all
-    const double gathered = nnz * seg * miss + (1.0 - miss) * used;
-    const double bytes = double(passes) * (a_bytes + gathered) + c_bytes;
-    const double lines = double((w * int64_t(sizeof(T)) + 127) / 128);
-    const double t_bytes = bytes / hbm, t_req = double(passes) * nnz * lines / req;
-    const double t = (t_bytes > t_req ? t_bytes : t_req) + double(passes) * launch;
-    if (t < best_t * 0.97) { // a further pass must buy at least 3 %
-      best_t = t;
-      best_w = w;
-    }
-  }
-  return best_w;
-}
-
+// (Column slicing — running the product as several passes over A, each against a column
+// slice of B — was built and measured in round 2 and removed: L2 allocates whole 128-byte
+// lines, so a 32- or 64-byte slice of a row-major B occupies as much of L2 as the full row
+// and every pass costs what the whole product costs (C3 k=32: 0.78 ms in one pass, 1.55 ms
+// in two, 3.07 ms in four; k=128: 2.55 -> 3.50 ms in four; profiles/
+// r02_spmm_column_slicing_negative.jsonl).)
 template <typename T, typename I, typename O>
 int pick_shape(spblas_b200_plan* p, const void* alpha, const void* values,
                const void* B, int64_t ldb, void* C, int64_t ldc, int64_t k) {
-  constexpr int V = 16 / sizeof(T);
-  const auto aligned16 = [](const void* q) {
-    return (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
-  };
-  const bool vec = (k % V == 0) && (ldb % V == 0) && (ldc % V == 0) && aligned16(B) &&
-                   aligned16(C);
-  const int64_t w = spmm_slice_width<T>(p, k, vec);
-  p->spmm_slices_last = (k + w - 1) / w;
-  if (w >= k)
-    return spmm_pass<T, I, O>(p, alpha, values, B, ldb, C, ldc, k);
-  for (int64_t c0 = 0; c0 < k; c0 += w) {
-    const int64_t kw = k - c0 < w ? k - c0 : w;
-    if (int rc = spmm_pass<T, I, O>(p, alpha, values, static_cast<const T*>(B) + c0, ldb,
-                                    static_cast<T*>(C) + c0, ldc, kw))
-      return rc;
-  }
-  return SPBLAS_B200_SUCCESS;
+  return spmm_pass<T, I, O>(p, alpha, values, B, ldb, C, ldc, k);
 }
 
 template <typename T>

@@ -151,10 +151,18 @@ struct ScatterArgs {
 struct BarrierArgs {
   int n;
   unsigned long long epoch;
+  unsigned long long timeout_ns; // how long a rank waits for a peer before it gives up
   unsigned long long* remote[kMaxPeers];
   const unsigned long long* local[kMaxPeers];
-  unsigned int* state; // [0] blocks done, [1] timeout flag
+  unsigned int* state;   // [0] blocks done
+  unsigned int* gave_up; // host-mapped: set when a wait timed out (the next execute fails)
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 template <typename T>
 __device__ __forceinline__ void multimem_store(T* p, T v) {
@@ -1238,6 +1246,7 @@ spmv_carry_fixup_kernel(const int64_t* __restrict__ carry_row,
                         const T alpha, const __grid_constant__ ScatterArgs<T> sc,
                         const __grid_constant__ BarrierArgs bar) {
   const int64_t t = fix_lo + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  bool stored_to_peer = false;
   if (t < fix_hi) {
     const int64_t r = carry_row[t];
     if (r >= 0 && !(t + 1 < num_tiles && carry_row[t + 1] == r)) {
@@ -1249,16 +1258,23 @@ spmv_carry_fixup_kernel(const int64_t* __restrict__ carry_row,
         sum += carry_val[j];
       const T v = y[r] + alpha * sum;
       y[r] = v;
-      if (sc.n > 0)
+      if (sc.n > 0) {
         scatter_store(sc, r, v);
+        stored_to_peer = true;
+      }
     }
   }
   if (bar.n == 0)
     return;
+  // Order: (this kernel's own peer stores) -> count -> flag.  The product kernel's peer stores
+  // are complete (kernel boundary on the stream); only a thread that stored to a peer HERE
+  // needs the system-scope fence, everyone else orders through the block counter.
   __shared__ bool s_last;
-  __threadfence_system(); // this thread's peer stores, before the count below
+  if (stored_to_peer)
+    __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     const unsigned done = atomicAdd(&bar.state[0], 1u);
     s_last = done == gridDim.x - 1;
     if (s_last)
@@ -1271,8 +1287,9 @@ spmv_carry_fixup_kernel(const int64_t* __restrict__ carry_row,
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(bar.remote[threadIdx.x]),
                "l"(bar.epoch)
                : "memory");
-  const long long t0 = clock64();
+  const unsigned long long t0 = global_timer_ns();
   unsigned long long seen = 0;
+  unsigned polls = 0;
   for (;;) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];"
                  : "=l"(seen)
@@ -1280,8 +1297,11 @@ spmv_carry_fixup_kernel(const int64_t* __restrict__ carry_row,
                  : "memory");
     if (seen >= bar.epoch)
       break;
-    if (clock64() - t0 > (1ll << 33)) { // a peer is gone (~4 s): do not hang the GPU
-      bar.state[1] = 1u;
+    if ((++polls & 1023u) == 0 && global_timer_ns() - t0 > bar.timeout_ns) {
+      // a peer is gone: do not hang the GPU.  The flag lives in host-mapped memory, where the
+      // next execute on this plan reads it without a synchronisation and FAILS (cabi.cu).
+      *reinterpret_cast<volatile unsigned int*>(bar.gave_up) = 1u;
+      __threadfence_system();
       break;
     }
   }
@@ -1319,7 +1339,9 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
   BarrierArgs bar;
   bar.n = p->barrier.n;
   bar.epoch = 0;
+  bar.timeout_ns = p->barrier_timeout_ms * 1000000ull;
   bar.state = static_cast<unsigned int*>(p->barrier_state.p);
+  bar.gave_up = p->barrier_gave_up_d;
   for (int d = 0; d < kMaxPeers; ++d) {
     bar.remote[d] = d < bar.n ? p->barrier.remote[d] : nullptr;
     bar.local[d] = d < bar.n ? p->barrier.local[d] : nullptr;
@@ -1577,6 +1599,15 @@ int run_spmv_tiles(spblas_b200_plan* p, int val_type, const void* alpha,
 int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
              const void* values, const void* x, void* y) {
   p->last_launches = 0;
+  // a fused barrier of an earlier execute gave up on a peer: that step's x was incomplete.
+  // (host-mapped flag: read without synchronising; cleared so that the caller can recover)
+  if (p->barrier_gave_up_h && *static_cast<volatile unsigned int*>(p->barrier_gave_up_h)) {
+    *static_cast<volatile unsigned int*>(p->barrier_gave_up_h) = 0u;
+    p->barrier_gave_up_seen = true;
+    return fail(p, SPBLAS_B200_CUDA_ERROR,
+                "fused exchange: a peer did not reach the barrier of an earlier step within "
+                "the timeout (SPBLAS_B200_BARRIER_TIMEOUT_MS); x of that step was incomplete");
+  }
   return run_spmv_tiles(p, val_type, alpha, values, x, y, 0, -1);
 }
 

@@ -116,9 +116,6 @@ class operation_info_t:
     @property
     def trsv_sweeps(self): return self._query_scalar(_cabi.Q_TRSV_SWEEPS)
     @property
-    def spmm_slices(self): return self._query_scalar(_cabi.Q_SPMM_SLICES)
-
-    @property
     def barrier_epoch(self): return self._query_scalar(_cabi.Q_BARRIER_EPOCH)
     @property
     def barrier_timeout(self): return self._query_scalar(_cabi.Q_BARRIER_TIMEOUT)

@@ -11,8 +11,9 @@ The inspect phase records the column interval [cmin, cmax] its block touches and
                  (banded matrices: 5-point Poisson needs g entries per neighbour), or
   * "allgather": every block to every rank (R-MAT and other unstructured matrices).
 
-On GPUs the exchange is FUSED into the product (`fused=True`, the default when the plan is
-given and NVLink peer memory can be mapped): both x replicas live in symmetric memory
+On GPUs the exchange can be FUSED into the product (`fused=True`; with `fused=None`, the
+default, both ways are timed for a few steps at set-up on the operator's own matrix and the
+faster one is kept — every rank takes the same decision): both x replicas live in symmetric memory
 (torch.distributed._symmetric_memory supplies the allocation and the peer mapping — plumbing),
 the SpMV kernels store every row a peer needs straight into that peer's next-x replica, and
 the carry fix-up kernel ends with the cross-GPU flag barrier (include/spblas_b200.h:
@@ -123,6 +124,8 @@ class ShardedSpMV:
         self.info = info
         self.fused = False
         self.fused_error = None
+        self.calibration = None
+        self._steps_since_check = 0
         want = fused if fused is not None else True
         if (want and info is not None and self.world > 1 and self.plan.mode != "none"
                 and torch.device(device).type == "cuda"):
@@ -135,6 +138,52 @@ class ShardedSpMV:
                 self.fused_error = repr(exc)
         if not self.fused:
             self.x = [torch.zeros(n, dtype=dtype, device=device) for _ in range(2)]
+        elif fused is None:
+            self._calibrate(device)
+
+    @property
+    def exchange_impl(self) -> str:
+        if self.world == 1 or self.plan.mode == "none":
+            return "none"
+        if not self.fused:
+            return "nccl " + ("batched send/recv of the halo" if self.plan.mode == "halo" else
+                              "allgather (one broadcast per block when the blocks differ)")
+        return ("fused: rows stored into the peers' x replicas by the SpMV kernels (" +
+                ("one NVLS multimem.st per row" if getattr(self, "multicast", False) else
+                 "peer stores over NVLink") + ") + flag barrier in the carry fix-up kernel")
+
+    def _calibrate(self, device, steps: int = 12):
+        """fused=None: time `steps` iterations each way on zeros (the kernels' time does not
+        depend on the values) and keep the faster exchange; MAX over ranks, so every rank
+        decides alike.  The NCCL path runs on the same symmetric buffers."""
+        saved = self.cur
+        times = {}
+        for mode in (True, False):
+            self.fused = mode
+            for _ in range(3):
+                self.step()
+            torch.cuda.synchronize(device)
+            dist.barrier(group=self.group)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                self.step()
+            e1.record()
+            torch.cuda.synchronize(device)
+            t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            times["fused" if mode else "nccl"] = float(t.item())
+        self.fused = times["fused"] <= times["nccl"]
+        self.calibration = {"ms_per_step": times, "kept": "fused" if self.fused else "nccl",
+                            "steps": steps}
+        if not self.fused:
+            self.info.set_scatter(())
+            self.info.set_barrier((), ())
+        self.cur = saved
+        for t in self.x:
+            t.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)
 
     # -- fused exchange: symmetric x replicas, peer destinations, flag barrier ----------
     def _setup_fused(self, n, dtype, device, multicast):
@@ -171,6 +220,21 @@ class ShardedSpMV:
                 self._dsts.append(([(ptrs[q] + self.r0 * itemsize, b0 - self.r0, e0 - self.r0)
                                     for q, b0, e0 in p.sends], False))
         self.multicast = bool(self._dsts[0][1])
+        # the C-ABI arguments of both ping-pong states, built once (a step then costs two
+        # plain foreign calls, no Python list handling)
+        import ctypes as C
+        from . import _cabi
+        self._lib = _cabi.lib()
+        self._bound = []
+        for dsts, mc in self._dsts:
+            k = len(dsts)
+            self._bound.append((k, (C.c_void_p * max(k, 1))(*[int(d[0]) for d in dsts]),
+                                (C.c_int64 * max(k, 1))(*[int(d[1]) for d in dsts]),
+                                (C.c_int64 * max(k, 1))(*[int(d[2]) for d in dsts]), 1 if mc else 0))
+        k = len(peers)
+        self._bound_barrier = (k, (C.c_void_p * max(k, 1))(*self._remote_slots),
+                               (C.c_void_p * max(k, 1))(*self._local_slots))
+        self._exchange_bound = None              # which ping-pong state the plan holds now
 
     def _gather_needs(self, col_range, device):
         if self.world == 1:
@@ -198,13 +262,24 @@ class ShardedSpMV:
         nxt = self.x[1 - self.cur]
         y = nxt[self.r0:self.r1]
         if self.fused:
-            if exchange:
-                dsts, mc = self._dsts[1 - self.cur]
-                self.info.set_scatter(dsts, multicast=mc)
-                self.info.set_barrier(self._remote_slots, self._local_slots)
-            else:
-                self.info.set_scatter(())
-                self.info.set_barrier((), ())
+            want = (1 - self.cur) if exchange else None
+            if want != self._exchange_bound:
+                if exchange:
+                    k, ptrs, lo, hi, mc = self._bound[want]
+                    st = self._lib.spblas_b200_plan_set_scatter(self.info._plan, k, ptrs, lo, hi, mc)
+                    if st == 0 and self._exchange_bound is None:
+                        kb, rs, ls = self._bound_barrier
+                        st = self._lib.spblas_b200_plan_set_barrier(self.info._plan, kb, rs, ls)
+                    if st != 0:
+                        raise RuntimeError("fused exchange: " + self.info._err())
+                else:
+                    self.info.set_scatter(())
+                    self.info.set_barrier((), ())
+                self._exchange_bound = want
+        elif getattr(self, "_exchange_bound", None) is not None:
+            self.info.set_scatter(())            # calibration left the plan in a fused state
+            self.info.set_barrier((), ())
+            self._exchange_bound = None
         self.local_multiply(self.x[self.cur], y)
         return y
 
