@@ -74,9 +74,8 @@ enum { SPBLAS_B200_F32 = 0, SPBLAS_B200_F64 = 1, SPBLAS_B200_S32 = 2 };
 /* inspect flags */
 enum {
   SPBLAS_B200_INSPECT_DEFAULT = 0,
-  /* Skip the row-length histogram (partition table only).  Used by the
-     no-`info` multiply(a, x, y) overload, which re-derives the partition on
-     every call because it may not assume the structure is unchanged. */
+  /* Skip the row-length histogram (partition table and validation of the offsets array
+     only).  Used by the no-`info` multiply(a, x, y) overloads. */
   SPBLAS_B200_INSPECT_LIGHT = 1
 };
 
@@ -222,10 +221,39 @@ SPBLAS_B200_API int spblas_b200_spmm(spblas_b200_plan* plan, int val_type,
                                      const void* d_B, int64_t ldb, void* d_C,
                                      int64_t ldc, int64_t k);
 
+/* The 4-argument multiply: y[m] = alpha * A * x[n] + beta * d[m]  and
+   C[m x k] = alpha * A * B + beta * D  (D row-major, leading dimension ldd >= k).
+   Replaces the form sketched in notes/matrices.hpp (multiply(a, b, c, d)) and implemented by
+   the reference only for SpGEMM on rocSPARSE, whose convention it follows
+   (vendor/rocsparse/multiply_spgemm.hpp:69-118: alpha = scaling factors of a and b,
+   beta = scaling factor of d, i.e. multiply(a, x, y, scaled(beta, d)); :276-283: the
+   3-argument form is the 4-argument one with beta = 0).  The addend is fused into the single
+   store every row of the result gets — no second pass over y.  d / D may alias y / C (the
+   solver update y = alpha A x + beta y).  beta is a HOST pointer; beta == 0 is exactly the
+   3-argument product: d is not read, so a NaN in it cannot reach the result. */
+SPBLAS_B200_API int spblas_b200_spmv_axpby(spblas_b200_plan* plan, int val_type,
+                                           const void* alpha, const void* d_values,
+                                           const void* d_x, const void* beta,
+                                           const void* d_d, void* d_y);
+SPBLAS_B200_API int spblas_b200_spmm_axpby(spblas_b200_plan* plan, int val_type,
+                                           const void* alpha, const void* d_values,
+                                           const void* d_B, int64_t ldb, const void* beta,
+                                           const void* d_D, int64_t ldd, void* d_C,
+                                           int64_t ldc, int64_t k);
+
 /* One-shot forms used by the overloads that take no operation_info_t
    (vendor/cusparse/spmv_impl.hpp:92-102 creates and destroys a cuSPARSE handle
-   per call there).  They run a LIGHT inspect on a thread-local cached plan
-   (buffers are reused, never assumed valid) and then execute. */
+   per call there).  They run on a thread-local plan whose buffers are reused.  A structure
+   is never ASSUMED unchanged: the first call on it runs a LIGHT inspect (partition +
+   validation of the offsets array, no histogram; two host synchronisations); a later SpMV
+   call with the same pointers, sizes and types reuses that plan after a DEVICE-side check —
+   one kernel recomputes a 64-bit fingerprint of the offsets array and compares it with the
+   stored one; the product's kernels are launched right behind it and return without
+   touching y unless it matches; the host reads the verdict from host-mapped memory (no
+   stream synchronisation) and falls back to the light inspect if the array changed in
+   place.  Steady state: one extra kernel over the offsets per call.
+   spblas_b200_once_release() frees the calling thread's one-shot plan (it is also freed when
+   the thread exits while the CUDA runtime is still loaded). */
 SPBLAS_B200_API int spblas_b200_spmv_once(
     void* cuda_stream, int format, int64_t m, int64_t n, int64_t nnz,
     const void* d_ptr, const void* d_ind, int off_type, int idx_type,
@@ -236,6 +264,19 @@ SPBLAS_B200_API int spblas_b200_spmm_once(
     const void* d_ptr, const void* d_ind, int off_type, int idx_type,
     int val_type, const void* alpha, const void* d_values, const void* d_B,
     int64_t ldb, void* d_C, int64_t ldc, int64_t k);
+/* ... and their 4-argument forms (y = alpha A x + beta d, C = alpha A B + beta D) */
+SPBLAS_B200_API int spblas_b200_spmv_axpby_once(
+    void* cuda_stream, int format, int64_t m, int64_t n, int64_t nnz,
+    const void* d_ptr, const void* d_ind, int off_type, int idx_type,
+    int val_type, const void* alpha, const void* d_values, const void* d_x,
+    const void* beta, const void* d_d, void* d_y);
+SPBLAS_B200_API int spblas_b200_spmm_axpby_once(
+    void* cuda_stream, int format, int64_t m, int64_t n, int64_t nnz,
+    const void* d_ptr, const void* d_ind, int off_type, int idx_type,
+    int val_type, const void* alpha, const void* d_values, const void* d_B,
+    int64_t ldb, const void* beta, const void* d_D, int64_t ldd, void* d_C,
+    int64_t ldc, int64_t k);
+SPBLAS_B200_API void spblas_b200_once_release(void);
 
 /* ---- triangular_solve(a, uplo, diag, b, x): x = inv(tri(A)) b -----------------
 

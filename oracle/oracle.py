@@ -132,6 +132,16 @@ def spmm(fmt, shape, ptr, ind, values, B, alpha_a=None, alpha_b=None, impl="orac
     return out
 
 
+def axpby(t, d, beta):
+    """The 4-argument multiply's epilogue, y = t + beta * d with t = the 3-argument product
+    (the convention of the reference's only 4-argument implementation,
+    vendor/rocsparse/multiply_spgemm.hpp:69-118: beta = scaling factor of d): one multiply and
+    one add per element, each rounded in the operands' type."""
+    t, d = np.asarray(t), np.asarray(d)
+    b = t.dtype.type(beta)
+    return (t + b * d.astype(t.dtype)).astype(t.dtype)
+
+
 def abs_rowsum(rowptr, colind, values, x, alpha=1.0):
     """s_i = sum_j |alpha a_ij x_j| in float64 (tolerance denominator)."""
     rowptr, colind, values, x = _c(rowptr), _c(colind), _c(values), _c(x)
@@ -195,20 +205,22 @@ def row_segments(rowptr, seg):
     return out[: 3 * n].reshape(-1, 3)
 
 
-def hub_columns(colind, n_cols, max_cols, min_count):
+def hub_columns(colind, n_cols, max_cols, min_count, by_popularity=False):
     """Definition of the hub-column analysis (csrc/hub.cu; no reference counterpart — the
     reference gathers x[j] per stored entry, multiply_impl.hpp:48-52): count the references
     per column, keep the columns referenced >= min_count times, order them by (count
     descending, column ascending), take the first max_cols, renumber them in ascending
     column order; a reference to hub number s is re-encoded as ~s.
-    Returns (hub columns ascending, references to them, encoded colind)."""
+    Returns (hub columns ascending, references to them, encoded colind).  by_popularity: the
+    table of the global-memory kernel instead — the hubs keep the (count descending, column
+    ascending) order, hub number s is the s-th most referenced column."""
     ci = np.asarray(colind).astype(np.int64)
     counts = np.bincount(ci, minlength=n_cols) if len(ci) else np.zeros(n_cols, np.int64)
     cand = np.nonzero(counts >= max(int(min_count), 1))[0]
     order = np.lexsort((cand, -counts[cand]))           # primary: count desc, then column asc
     top = cand[order][: int(max_cols)]
     refs = int(counts[top].sum())
-    hubs = np.sort(top)
+    hubs = top if by_popularity else np.sort(top)
     slot = np.full(n_cols, -1, dtype=np.int64)
     slot[hubs] = np.arange(len(hubs))
     enc = np.where(slot[ci] >= 0, ~slot[ci], ci).astype(np.int32) if len(ci) else ci.astype(np.int32)

@@ -84,10 +84,20 @@ def run_spmv(wl, reps):
     from spblas_reference_b200 import _cabi
     sets = spmv_workload(wl)
     ops = []
+    opt = os.environ.get("EXP_MATRIX_OPT", "0") == "1"      # wrap in matrix_opt (hub tables)
+    force = os.environ.get("EXP_VARIANT")                   # force a kernel variant
+    hub_cols = os.environ.get("EXP_HUB_COLS")
     for v, rp, ci, shape, x in sets:
         a = sb.csr_view(v, rp, ci, shape, int(ci.numel()))
+        if opt:
+            a = sb.matrix_opt(a)
         y = torch.empty(shape[0], dtype=v.dtype, device=v.device)
-        ops.append((a, x, y, sb.multiply_inspect(a, x, y)))
+        info = sb.multiply_inspect(a, x, y)
+        if force is not None:
+            if int(force) >= 3:
+                info.set_hub(True, int(hub_cols) if hub_cols else 0, 0)
+            info.force_spmv_variant(int(force))
+        ops.append((a, x, y, info))
 
     def fn(i):
         a, x, y, info = ops[i % len(ops)]
@@ -98,7 +108,9 @@ def run_spmv(wl, reps):
     sT = v.element_size()
     nbytes = nnz * (sT + 4) + (shape[0] + 1) * rp.element_size() + shape[1] * sT + shape[0] * sT
     print(json.dumps({"exp": "spmv", "workload": wl, "lib": os.path.basename(_cabi.LIB_PATH),
-                      "variant": info.spmv_variant, "ms": round(ms, 4), "nnz": nnz,
+                      "variant": info.spmv_variant, "matrix_opt": opt, "forced": force,
+                      "hub_count": info.hub_count, "hub_ref_share": round(info.hub_refs / max(nnz, 1), 4),
+                      "ms": round(ms, 4), "nnz": nnz,
                       "rows": shape[0], "cols": shape[1],
                       "gflops": round(2.0 * nnz / ms / 1e6, 1),
                       "alg_gbs": round(nbytes / ms / 1e6, 1),

@@ -42,6 +42,8 @@ SYMBOLS = (
     "spblas_b200_transpose_inspect", "spblas_b200_transpose",
     "spblas_b200_plan_cache_values", "spblas_b200_trsv_inspect", "spblas_b200_trsv",
     "spblas_b200_plan_set_hub",
+    "spblas_b200_spmv_axpby", "spblas_b200_spmm_axpby",
+    "spblas_b200_spmv_axpby_once", "spblas_b200_spmm_axpby_once", "spblas_b200_once_release",
 )
 
 
@@ -111,6 +113,18 @@ def lib() -> C.CDLL:
     L.spblas_b200_spmm_once.argtypes = [vp, i32, i64, i64, i64, vp, vp, i32, i32, i32, vp,
                                         vp, vp, i64, vp, i64, i64]
     L.spblas_b200_spmm_once.restype = i32
+    L.spblas_b200_spmv_axpby.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    L.spblas_b200_spmv_axpby.restype = i32
+    L.spblas_b200_spmm_axpby.argtypes = [vp, i32, vp, vp, vp, i64, vp, vp, i64, vp, i64, i64]
+    L.spblas_b200_spmm_axpby.restype = i32
+    L.spblas_b200_spmv_axpby_once.argtypes = [vp, i32, i64, i64, i64, vp, vp, i32, i32, i32, vp,
+                                              vp, vp, vp, vp, vp]
+    L.spblas_b200_spmv_axpby_once.restype = i32
+    L.spblas_b200_spmm_axpby_once.argtypes = [vp, i32, i64, i64, i64, vp, vp, i32, i32, i32, vp,
+                                              vp, vp, i64, vp, vp, i64, vp, i64, i64]
+    L.spblas_b200_spmm_axpby_once.restype = i32
+    L.spblas_b200_once_release.argtypes = []
+    L.spblas_b200_once_release.restype = None
     L.spblas_b200_plan_query.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.spblas_b200_plan_query.restype = i32
     L.spblas_b200_last_error.argtypes = [vp]

@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "plan.hpp"
 
 namespace b200 {
@@ -68,10 +70,14 @@ void release_all(spblas_b200_plan* p) {
                           &p->spmm_carry_row, &p->spmm_carry_val, &p->barrier_state,
                           &p->ws_starts, &p->ws_carry_row, &p->ws_carry_val, &p->own_values,
                           &p->trsv_level, &p->trsv_order, &p->trsv_tmp0, &p->trsv_tmp1,
-                          &p->trsv_level_ptr, &p->hub_cols, &p->hub_colind};
+                          &p->trsv_level_ptr, &p->hub_cols, &p->hub_colind, &p->hub_x};
   for (DeviceBuffer* b : bufs)
     release(*b);
   release(p->hc_colmax);
+  if (p->fp_status_h)
+    cudaFreeHost(p->fp_status_h);
+  p->fp_status_h = p->fp_status_d = nullptr;
+  release(p->fp_state);
   if (p->barrier_gave_up_h)
     cudaFreeHost(p->barrier_gave_up_h);
   p->barrier_gave_up_h = p->barrier_gave_up_d = nullptr;
@@ -107,12 +113,38 @@ struct CachedValues {
   ~CachedValues() { p->csr_perm = saved_perm; }
 };
 
+// NVTX range around every entry point that launches work (the reference has
+// log_trace only).  Header-only NVTX3: a no-op costing nanoseconds unless a tool is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 thread_local std::string g_once_error;
+// The one-shot plan of the overloads that take no operation_info_t, one per host thread.  It
+// keeps the LAST structure's plan and its key; a call with the same key runs on the cached
+// plan after a device-side check that the offsets array is unchanged (inspect.cu 1b).
+struct OnceKey {
+  int format = -1, off_type = 0, idx_type = 0;
+  int64_t m = 0, n = 0, nnz = 0;
+  const void* ptr = nullptr;
+  const void* ind = nullptr;
+  bool operator==(const OnceKey& o) const {
+    return format == o.format && off_type == o.off_type && idx_type == o.idx_type && m == o.m &&
+           n == o.n && nnz == o.nnz && ptr == o.ptr && ind == o.ind;
+  }
+};
 struct OncePlanHolder {
   spblas_b200_plan* plan = nullptr;
+  bool cached = false; // plan holds the light-inspected structure of `key`
+  OnceKey key;
   ~OncePlanHolder() {
-    // The CUDA context may already be gone at thread/process exit; leak the
-    // device buffers rather than call into a dead runtime.
+    // Thread exit: give the device buffers back while the runtime is still there (at process
+    // exit it may already be unloading: then the context takes everything with it).
+    if (plan && cudaFree(nullptr) == cudaSuccess)
+      spblas_b200_plan_destroy(plan);
     plan = nullptr;
   }
 };
@@ -330,6 +362,7 @@ int spblas_b200_inspect(spblas_b200_plan* p, int format, int64_t m, int64_t n,
                         int off_type, int idx_type, int64_t k_hint, int flags) {
   if (!p)
     return SPBLAS_B200_INVALID_ARGUMENT;
+  NvtxRange nvtx_range("spblas_b200_inspect");
   p->err.clear();
   p->inspected = false;
   p->host_chunks = 0; // the chunk table belongs to the previous structure
@@ -375,6 +408,7 @@ int spblas_b200_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
                      const void* d_values, const void* d_x, void* d_y) {
   if (!p)
     return SPBLAS_B200_INVALID_ARGUMENT;
+  NvtxRange nvtx_range("spblas_b200_spmv");
   p->err.clear();
   if (!p->inspected)
     return fail(p, SPBLAS_B200_NOT_INSPECTED, "spmv called before inspect");
@@ -389,9 +423,80 @@ int spblas_b200_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
   return run_spmv(p, val_type, alpha, d_values, d_x, d_y);
 }
 
+namespace {
+// the addend of one execute: set for the duration of the call only
+struct AddendScope {
+  spblas_b200_plan* p;
+  AddendScope(spblas_b200_plan* plan, int val_type, const void* beta, const void* d_d,
+              int64_t ldd)
+      : p(plan) {
+    p->epi_d = d_d;
+    p->epi_ldd = ldd;
+    std::memcpy(p->epi_beta, beta, b200::type_size_val(val_type));
+  }
+  ~AddendScope() {
+    p->epi_d = nullptr;
+    p->epi_ldd = 0;
+  }
+};
+
+// beta == 0 is "no addend": d is not read at all (a NaN in it must not reach y, exactly as
+// stale contents of y never do)
+bool beta_is_zero(int val_type, const void* beta) {
+  switch (val_type) {
+  case SPBLAS_B200_F32:
+    return *static_cast<const float*>(beta) == 0.0f;
+  case SPBLAS_B200_F64:
+    return *static_cast<const double*>(beta) == 0.0;
+  default:
+    return *static_cast<const int32_t*>(beta) == 0;
+  }
+}
+} // namespace
+
+int spblas_b200_spmv_axpby(spblas_b200_plan* p, int val_type, const void* alpha,
+                           const void* d_values, const void* d_x, const void* beta,
+                           const void* d_d, void* d_y) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  if (!valid_value_type(val_type))
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "value type must be f32, f64 or s32");
+  if (!beta)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "beta is null");
+  if (beta_is_zero(val_type, beta))
+    return spblas_b200_spmv(p, val_type, alpha, d_values, d_x, d_y);
+  if (p->inspected && p->m > 0 && !d_d)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null device pointer (d)");
+  AddendScope addend(p, val_type, beta, d_d, 0);
+  return spblas_b200_spmv(p, val_type, alpha, d_values, d_x, d_y);
+}
+
+int spblas_b200_spmm_axpby(spblas_b200_plan* p, int val_type, const void* alpha,
+                           const void* d_values, const void* d_B, int64_t ldb,
+                           const void* beta, const void* d_D, int64_t ldd, void* d_C,
+                           int64_t ldc, int64_t k) {
+  if (!p)
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  p->err.clear();
+  if (!valid_value_type(val_type))
+    return fail(p, SPBLAS_B200_NOT_SUPPORTED, "value type must be f32, f64 or s32");
+  if (!beta)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "beta is null");
+  if (beta_is_zero(val_type, beta))
+    return spblas_b200_spmm(p, val_type, alpha, d_values, d_B, ldb, d_C, ldc, k);
+  if (ldd < k)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "leading dimension smaller than k");
+  if (p->inspected && p->m > 0 && k > 0 && !d_D)
+    return fail(p, SPBLAS_B200_INVALID_ARGUMENT, "null device pointer (D)");
+  AddendScope addend(p, val_type, beta, d_D, ldd);
+  return spblas_b200_spmm(p, val_type, alpha, d_values, d_B, ldb, d_C, ldc, k);
+}
+
 int spblas_b200_plan_cache_values(spblas_b200_plan* p, int val_type, const void* d_values) {
   if (!p)
     return SPBLAS_B200_INVALID_ARGUMENT;
+  NvtxRange nvtx_range("spblas_b200_plan_cache_values");
   p->err.clear();
   p->cached_values = false;
   if (!d_values)
@@ -417,6 +522,7 @@ int spblas_b200_trsv_inspect(spblas_b200_plan* p, int64_t m, int64_t nnz,
                              int idx_type, int upper, int unit_diagonal) {
   if (!p)
     return SPBLAS_B200_INVALID_ARGUMENT;
+  NvtxRange nvtx_range("spblas_b200_trsv_inspect");
   p->err.clear();
   p->trsv_ready = false;
   if (!valid_index_type(off_type) || !valid_index_type(idx_type))
@@ -450,6 +556,7 @@ int spblas_b200_trsv(spblas_b200_plan* p, int val_type, const void* alpha_a,
                      void* d_x) {
   if (!p)
     return SPBLAS_B200_INVALID_ARGUMENT;
+  NvtxRange nvtx_range("spblas_b200_trsv");
   p->err.clear();
   if (!p->trsv_ready)
     return fail(p, SPBLAS_B200_NOT_INSPECTED, "trsv called before trsv_inspect");
@@ -471,6 +578,7 @@ int spblas_b200_transpose(spblas_b200_plan* p, int val_type, const void* d_value
                           void* d_t_rowptr, void* d_t_colind, void* d_t_values) {
   if (!p)
     return SPBLAS_B200_INVALID_ARGUMENT;
+  NvtxRange nvtx_range("spblas_b200_transpose");
   p->err.clear();
   if (!p->inspected || p->format != SPBLAS_B200_CSC)
     return fail(p, SPBLAS_B200_NOT_INSPECTED, "transpose called before transpose_inspect");
@@ -486,6 +594,7 @@ int spblas_b200_spmv_host(spblas_b200_plan* p, int val_type, const void* alpha,
                           void* d_x, void* d_y) {
   if (!p)
     return SPBLAS_B200_INVALID_ARGUMENT;
+  NvtxRange nvtx_range("spblas_b200_spmv_host");
   p->err.clear();
   if (!p->inspected)
     return fail(p, SPBLAS_B200_NOT_INSPECTED, "spmv_host called before inspect");
@@ -505,6 +614,7 @@ int spblas_b200_spmm(spblas_b200_plan* p, int val_type, const void* alpha,
                      void* d_C, int64_t ldc, int64_t k) {
   if (!p)
     return SPBLAS_B200_INVALID_ARGUMENT;
+  NvtxRange nvtx_range("spblas_b200_spmm");
   p->err.clear();
   if (!p->inspected)
     return fail(p, SPBLAS_B200_NOT_INSPECTED, "spmm called before inspect");
@@ -535,6 +645,7 @@ static int once_plan(void* stream, spblas_b200_plan** out) {
     // buffers belong to another device: start over on this one
     spblas_b200_plan_destroy(g_once.plan);
     g_once.plan = nullptr;
+    g_once.cached = false;
     int rc = spblas_b200_plan_create(&g_once.plan, stream);
     if (rc) {
       g_once_error = "could not create the one-shot plan";
@@ -546,23 +657,139 @@ static int once_plan(void* stream, spblas_b200_plan** out) {
   return SPBLAS_B200_SUCCESS;
 }
 
-int spblas_b200_spmv_once(void* stream, int format, int64_t m, int64_t n,
-                          int64_t nnz, const void* d_ptr, const void* d_ind,
-                          int off_type, int idx_type, int val_type,
-                          const void* alpha, const void* d_values,
-                          const void* d_x, void* d_y) {
+// Waits (without a stream synchronisation) for the verify kernel of call `seq` to report:
+// 1 unchanged, 0 changed, -1 the stream failed or never ran it.
+static int await_verdict(spblas_b200_plan* p, unsigned int seq) {
+  volatile unsigned long long* st = p->fp_status_h;
+  for (unsigned long long spins = 0;; ++spins) {
+    const unsigned long long v = *st;
+    if ((v >> 1) == seq)
+      return int(v & 1ull);
+    if ((spins & 0xfffffull) == 0xfffffull) { // every ~1M polls: is the stream still alive?
+      const cudaError_t e = cudaStreamQuery(p->stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady)
+        return -1;
+      if (e == cudaSuccess && ((*st) >> 1) != seq)
+        return -1; // everything ran, the verdict never came (e.g. a captured stream)
+    }
+  }
+}
+
+static int spmv_once_impl(void* stream, int format, int64_t m, int64_t n, int64_t nnz,
+                          const void* d_ptr, const void* d_ind, int off_type, int idx_type,
+                          int val_type, const void* alpha, const void* d_values,
+                          const void* d_x, const void* beta, const void* d_d, void* d_y) {
   g_once_error.clear();
   spblas_b200_plan* p = nullptr;
   int rc = once_plan(stream, &p);
   if (rc)
     return rc;
+  auto execute = [&]() {
+    return beta ? spblas_b200_spmv_axpby(p, val_type, alpha, d_values, d_x, beta, d_d, d_y)
+                : spblas_b200_spmv(p, val_type, alpha, d_values, d_x, d_y);
+  };
+  OnceKey key;
+  key.format = format, key.off_type = off_type, key.idx_type = idx_type;
+  key.m = m, key.n = n, key.nnz = nnz, key.ptr = d_ptr, key.ind = d_ind;
+  // ---- the structure of the previous call, if the offsets array still holds what it held ----
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(p->stream, &cap);
+  if (g_once.cached && key == g_once.key && format == SPBLAS_B200_CSR && m > 0 &&
+      p->fp_status_h && cap == cudaStreamCaptureStatusNone) {
+    const unsigned int seq = ++p->fp_seq == 0 ? ++p->fp_seq : p->fp_seq;
+    p->inspected = true;
+    rc = verify_structure(p, seq);
+    if (rc == SPBLAS_B200_SUCCESS) {
+      // the product is launched at once, behind the check: its kernels return without
+      // touching y unless the check opens the gate
+      p->gate = structure_gate(p);
+      p->gate_value = seq;
+      rc = execute();
+      p->gate = nullptr;
+      const int verdict = rc == SPBLAS_B200_SUCCESS ? await_verdict(p, seq) : -1;
+      p->inspected = false;
+      if (rc == SPBLAS_B200_SUCCESS && verdict == 1)
+        return SPBLAS_B200_SUCCESS;
+    }
+    p->inspected = false;
+    g_once.cached = false; // changed in place (or the check could not run): start over
+  }
+  // ---- a structure not seen before: light inspect (validates, leaves the fingerprint) --------
+  g_once.cached = false;
+  if (!p->fp_status_h) {
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
+      p->fp_status_h = static_cast<unsigned long long*>(h);
+      *p->fp_status_h = 0;
+      void* d = nullptr;
+      if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess)
+        p->fp_status_d = static_cast<unsigned long long*>(d);
+    }
+  }
   rc = spblas_b200_inspect(p, format, m, n, nnz, d_ptr, d_ind, off_type, idx_type,
                            1, SPBLAS_B200_INSPECT_LIGHT);
   if (rc == SPBLAS_B200_SUCCESS)
-    rc = spblas_b200_spmv(p, val_type, alpha, d_values, d_x, d_y);
+    rc = execute();
   if (rc)
     g_once_error = p->err;
-  // the one-shot plan must not outlive the caller's structure pointers
+  else if (p->fp_status_d) {
+    g_once.cached = true; // the next call may reuse this plan — after the device-side check
+    g_once.key = key;
+  }
+  // the one-shot plan never trusts the caller's structure pointers between calls
+  p->inspected = false;
+  return rc;
+}
+
+int spblas_b200_spmv_once(void* stream, int format, int64_t m, int64_t n,
+                          int64_t nnz, const void* d_ptr, const void* d_ind,
+                          int off_type, int idx_type, int val_type,
+                          const void* alpha, const void* d_values,
+                          const void* d_x, void* d_y) {
+  return spmv_once_impl(stream, format, m, n, nnz, d_ptr, d_ind, off_type, idx_type, val_type,
+                        alpha, d_values, d_x, nullptr, nullptr, d_y);
+}
+
+int spblas_b200_spmv_axpby_once(void* stream, int format, int64_t m, int64_t n,
+                                int64_t nnz, const void* d_ptr, const void* d_ind,
+                                int off_type, int idx_type, int val_type,
+                                const void* alpha, const void* d_values, const void* d_x,
+                                const void* beta, const void* d_d, void* d_y) {
+  if (!beta) {
+    g_once_error = "beta is null";
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  }
+  return spmv_once_impl(stream, format, m, n, nnz, d_ptr, d_ind, off_type, idx_type, val_type,
+                        alpha, d_values, d_x, beta, d_d, d_y);
+}
+
+void spblas_b200_once_release(void) {
+  if (g_once.plan)
+    spblas_b200_plan_destroy(g_once.plan);
+  g_once.plan = nullptr;
+  g_once.cached = false;
+}
+
+static int spmm_once_impl(void* stream, int format, int64_t m, int64_t n, int64_t nnz,
+                          const void* d_ptr, const void* d_ind, int off_type, int idx_type,
+                          int val_type, const void* alpha, const void* d_values,
+                          const void* d_B, int64_t ldb, const void* beta, const void* d_D,
+                          int64_t ldd, void* d_C, int64_t ldc, int64_t k) {
+  g_once_error.clear();
+  spblas_b200_plan* p = nullptr;
+  int rc = once_plan(stream, &p);
+  if (rc)
+    return rc;
+  g_once.cached = false; // the plan is about to hold another structure
+  // SpMM wants to know about very long rows, so this is a full inspect.
+  rc = spblas_b200_inspect(p, format, m, n, nnz, d_ptr, d_ind, off_type, idx_type,
+                           k, SPBLAS_B200_INSPECT_DEFAULT);
+  if (rc == SPBLAS_B200_SUCCESS)
+    rc = beta ? spblas_b200_spmm_axpby(p, val_type, alpha, d_values, d_B, ldb, beta, d_D, ldd,
+                                       d_C, ldc, k)
+              : spblas_b200_spmm(p, val_type, alpha, d_values, d_B, ldb, d_C, ldc, k);
+  if (rc)
+    g_once_error = p->err;
   p->inspected = false;
   return rc;
 }
@@ -573,20 +800,22 @@ int spblas_b200_spmm_once(void* stream, int format, int64_t m, int64_t n,
                           const void* alpha, const void* d_values,
                           const void* d_B, int64_t ldb, void* d_C, int64_t ldc,
                           int64_t k) {
-  g_once_error.clear();
-  spblas_b200_plan* p = nullptr;
-  int rc = once_plan(stream, &p);
-  if (rc)
-    return rc;
-  // SpMM wants to know about very long rows, so this is a full inspect.
-  rc = spblas_b200_inspect(p, format, m, n, nnz, d_ptr, d_ind, off_type, idx_type,
-                           k, SPBLAS_B200_INSPECT_DEFAULT);
-  if (rc == SPBLAS_B200_SUCCESS)
-    rc = spblas_b200_spmm(p, val_type, alpha, d_values, d_B, ldb, d_C, ldc, k);
-  if (rc)
-    g_once_error = p->err;
-  p->inspected = false;
-  return rc;
+  return spmm_once_impl(stream, format, m, n, nnz, d_ptr, d_ind, off_type, idx_type, val_type,
+                        alpha, d_values, d_B, ldb, nullptr, nullptr, 0, d_C, ldc, k);
+}
+
+int spblas_b200_spmm_axpby_once(void* stream, int format, int64_t m, int64_t n,
+                                int64_t nnz, const void* d_ptr, const void* d_ind,
+                                int off_type, int idx_type, int val_type,
+                                const void* alpha, const void* d_values, const void* d_B,
+                                int64_t ldb, const void* beta, const void* d_D, int64_t ldd,
+                                void* d_C, int64_t ldc, int64_t k) {
+  if (!beta) {
+    g_once_error = "beta is null";
+    return SPBLAS_B200_INVALID_ARGUMENT;
+  }
+  return spmm_once_impl(stream, format, m, n, nnz, d_ptr, d_ind, off_type, idx_type, val_type,
+                        alpha, d_values, d_B, ldb, beta, d_D, ldd, d_C, ldc, k);
 }
 
 const char* spblas_b200_last_error(const spblas_b200_plan* p) {

@@ -24,8 +24,10 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include "device_utils.cuh"
 #include "plan.hpp"
@@ -91,6 +93,10 @@ int launch_check(spblas_b200_plan* p, const char* what) {
   return e == cudaSuccess ? SPBLAS_B200_SUCCESS : cuda_fail(p, e, what);
 }
 
+struct ToInt64 {
+  __device__ __forceinline__ int64_t operator()(const int& v) const { return int64_t(v); }
+};
+
 struct Scratch { // freed when the analysis returns, however it returns
   DeviceBuffer counts, cand, cand_counts, sorted_counts, sorted_cols, ws, nsel;
   ~Scratch() {
@@ -119,11 +125,23 @@ int64_t hub_capacity(const spblas_b200_plan* p, size_t val_bytes, int walk_warps
   return std::min(hw, columns(int64_t(163) * 1024));
 }
 
-int build_hub_table(spblas_b200_plan* p, int64_t cap) {
+// How many columns the GLOBAL-memory table holds (spmv_hubg_stream_kernel): half of L2 —
+// the table is what should stay resident beside the streams of A.
+int64_t hub_global_capacity(const spblas_b200_plan* p, size_t val_bytes) {
+  if (p->hub_cap_override > 0)
+    return p->hub_cap_override;
+  return (p->l2_bytes / 2) / int64_t(val_bytes);
+}
+
+// by_popularity = false: the table of the shared-memory kernel (hubs in ascending column
+// order); true: the table of the global-memory kernel (hubs in descending popularity, ties in
+// ascending column order — the hottest entries share cache lines, so L1 holds the top of it).
+int build_hub_table(spblas_b200_plan* p, int64_t cap, bool by_popularity) {
   p->hub_state = -1;
   p->hub_count = 0;
   p->hub_refs = 0;
   p->hub_cap = cap;
+  p->hub_by_popularity = by_popularity;
   if (p->idx_type != SPBLAS_B200_I32)
     return SPBLAS_B200_SUCCESS; // no hubs: the caller falls back to the warp-stream kernel
   const int64_t nnz = p->nnz, cols = p->csr_cols;
@@ -148,8 +166,12 @@ int build_hub_table(spblas_b200_plan* p, int64_t cap) {
     if (int rc = launch_check(p, "hub_count_kernel"))
       return rc;
     // candidates: columns referenced at least min_count times, in ascending order
+    // shared-memory table: a hub costs one load per CTA and launch; global table: one
+    // gather per launch, repaid from the second reference on
     const int min_count = int(std::min<int64_t>(
-        p->hub_min_count > 0 ? p->hub_min_count : 2 * int64_t(p->num_sms), 0x7fffffff));
+        p->hub_min_count > 0 ? p->hub_min_count
+                             : (by_popularity ? int64_t(3) : 2 * int64_t(p->num_sms)),
+        0x7fffffff));
     if (int rc = reserve(p, t.cand, size_t(cols) * sizeof(int32_t)))
       return rc;
     if (int rc = reserve(p, t.nsel, sizeof(int64_t)))
@@ -191,6 +213,36 @@ int build_hub_table(spblas_b200_plan* p, int64_t cap) {
                            t.ws.p, ws_bytes, cand_counts, sorted_counts, cand, sorted_cols,
                            int(nsel), 0, 32, s));
       const int64_t h = std::min<int64_t>(nsel, cap);
+      if (by_popularity) {
+        // millions of hubs: everything stays on the device.  refs = sum of the top h counts
+        cub::TransformInputIterator<int64_t, ToInt64, const int*> as64(sorted_counts, ToInt64());
+        ws_bytes = 0;
+        B200_CUDA_TRY(p, cub::DeviceReduce::Sum(nullptr, ws_bytes, as64, d_nsel, int(h), s));
+        if (int rc = reserve(p, t.ws, ws_bytes))
+          return rc;
+        B200_CUDA_TRY(p, cub::DeviceReduce::Sum(t.ws.p, ws_bytes, as64, d_nsel, int(h), s));
+        B200_CUDA_TRY(p, cudaMemcpyAsync(&refs, d_nsel, sizeof(refs), cudaMemcpyDeviceToHost, s));
+        if (int rc = reserve(p, p->hub_cols, size_t(std::max<int64_t>(h, 1)) * sizeof(int32_t)))
+          return rc;
+        B200_CUDA_TRY(p, cudaMemcpyAsync(p->hub_cols.p, sorted_cols, size_t(h) * sizeof(int32_t),
+                                         cudaMemcpyDeviceToDevice, s));
+        B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+        B200_CUDA_TRY(p, cudaMemsetAsync(counts, 0xff, size_t(cols) * sizeof(int), s));
+        if (h > 0) {
+          hub_slot_kernel<<<unsigned((h + 255) / 256), 256, 0, s>>>(
+              static_cast<const int32_t*>(p->hub_cols.p), h, counts);
+          if (int rc = launch_check(p, "hub_slot_kernel"))
+            return rc;
+        }
+        hub_encode_kernel<<<sweep_grid, 256, 0, s>>>(colind, nnz, cols, counts, pad, enc);
+        if (int rc = launch_check(p, "hub_encode_kernel"))
+          return rc;
+        B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+        p->hub_count = h;
+        p->hub_refs = refs;
+        p->hub_state = 1;
+        return SPBLAS_B200_SUCCESS;
+      }
       std::vector<int> top_counts(size_t(h), 0);
       hub.resize(size_t(h));
       B200_CUDA_TRY(p, cudaMemcpyAsync(top_counts.data(), sorted_counts, size_t(h) * sizeof(int),

@@ -47,6 +47,11 @@ enum SpmvVariant : int {
   // memory: one CTA of 32 warps per SM, a plan-owned re-encoded copy of colind (hub.cu).
   // For matrices with skewed column popularity (R-MAT); int32 indices only.
   kVariantHubStream = 3,
+  // the warp-stream walk with x at the most referenced columns gathered, once per product,
+  // into a compact table in GLOBAL memory (half of L2, hottest entries first) through the same
+  // re-encoded colind: for matrices whose x is larger than L2, where a gather that misses L2
+  // costs a 32-byte DRAM sector (C5: R-MAT scale 27, x = 1.07 GB).  int32 indices only.
+  kVariantHubGlobal = 4,
 };
 
 struct DeviceBuffer {
@@ -179,6 +184,8 @@ struct spblas_b200_plan {
   int64_t hub_cap = 0;         // capacity (columns) the table was built for
   int64_t hub_cap_override = 0; // env SPBLAS_B200_HUB_COLS / set_hub (0: what shared memory holds)
   int64_t hub_min_count = 0;   // env SPBLAS_B200_HUB_MIN_COUNT / set_hub (0: 2 x SM count)
+  bool hub_by_popularity = false; // the table's order: false ascending column (shared-memory kernel), true descending popularity (global-memory kernel)
+  b200::DeviceBuffer hub_x;    // global-memory kernel: x at the hub columns, refilled by every product
   int64_t hub_count = 0;       // H
   int64_t hub_refs = 0;        // nonzeros that reference a hub column
   bool light_inspect = false;  // the current structure came from a LIGHT inspect (no-info overloads)
@@ -219,6 +226,22 @@ struct spblas_b200_plan {
   std::vector<cudaEvent_t> hc_events; // 2 per chunk + 2
   int host_chunks_override = 0;       // env SPBLAS_B200_HOST_CHUNKS
 
+  // ---- structure cache of the one-shot plan (spblas_b200_spmv_once; inspect.cu 1b) -----
+  b200::DeviceBuffer fp_state;                 // HashState: fingerprint of the offsets, gate
+  unsigned long long* fp_status_h = nullptr;   // host-mapped: (seq << 1) | same, written by the verify kernel
+  unsigned long long* fp_status_d = nullptr;
+  unsigned int fp_seq = 0;                     // verified calls so far
+  // the kernels of a call that runs on a cached structure check *gate == gate_value first
+  // and return without touching y otherwise (nullptr: no gate)
+  const unsigned int* gate = nullptr;
+  unsigned int gate_value = 0;
+
+  // ---- addend of the running execute (4-argument multiply: y = alpha A x + beta d) -------
+  // set by the *_axpby entry points for the duration of one call; nullptr: beta = 0
+  const void* epi_d = nullptr;
+  int64_t epi_ldd = 0;                  // SpMM: leading dimension of D
+  alignas(8) unsigned char epi_beta[8] = {0};
+
   int forced_variant = -1;
   int spmv_variant = b200::kVariantMergeTile;
   int spmm_variant = 0;
@@ -245,6 +268,8 @@ void release(DeviceBuffer& b);
 
 // inspect.cu
 int inspect_structure(spblas_b200_plan* p, int flags);
+int verify_structure(spblas_b200_plan* p, unsigned int seq);
+const unsigned int* structure_gate(const spblas_b200_plan* p);
 int build_stream_partition(spblas_b200_plan* p, int64_t streams);
 int build_ws_partition(spblas_b200_plan* p, int64_t resident_warps);
 int run_transpose(spblas_b200_plan* p, int val_type, const void* values, void* t_rowptr,
@@ -254,7 +279,8 @@ int build_column_structure(spblas_b200_plan* p, int64_t m, int64_t nnz, const vo
 int gather_permuted_values(spblas_b200_plan* p, int val_type, const void* values, void* out);
 // hub.cu
 int64_t hub_capacity(const spblas_b200_plan* p, size_t val_bytes, int walk_warps);
-int build_hub_table(spblas_b200_plan* p, int64_t cap);
+int64_t hub_global_capacity(const spblas_b200_plan* p, size_t val_bytes);
+int build_hub_table(spblas_b200_plan* p, int64_t cap, bool by_popularity);
 // spmv.cu
 int run_spmv(spblas_b200_plan* p, int val_type, const void* alpha,
              const void* values, const void* x, void* y);

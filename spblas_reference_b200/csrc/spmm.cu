@@ -47,6 +47,18 @@ __device__ __forceinline__ BVec<T, VEC> load_b(const T* p) {
   return r;
 }
 
+// the addend D of C = alpha A B + beta D: plain (coherent) loads — D may alias C
+template <typename T, int VEC>
+__device__ __forceinline__ BVec<T, VEC> load_d(const T* p) {
+  BVec<T, VEC> r;
+  if constexpr (VEC == 1) {
+    r.v[0] = *p;
+  } else {
+    *reinterpret_cast<uint4*>(&r.v[0]) = *reinterpret_cast<const uint4*>(p);
+  }
+  return r;
+}
+
 template <typename T, int VEC>
 __device__ __forceinline__ void store_c(T* p, const BVec<T, VEC>& r) {
   if constexpr (VEC == 1) {
@@ -134,7 +146,8 @@ spmm_row_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
                 const T* __restrict__ values, const O* __restrict__ perm,
                 const T* __restrict__ B, const int64_t ldb, T* __restrict__ C,
                 const int64_t ldc, const T alpha, const int64_t rows,
-                const int64_t k, const int64_t seg_limit) {
+                const int64_t k, const int64_t seg_limit, const T* D, const int64_t ldd,
+                const T beta) {
   constexpr int GROUPS = kSpmmThreads / LANES;
   constexpr int E = ChunkShape<LANES>::E;
   constexpr int CHUNK = ChunkShape<LANES>::CHUNK;
@@ -194,6 +207,12 @@ spmm_row_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
 #pragma unroll
         for (int u = 0; u < VEC; ++u)
           out.v[u] = alpha * acc[u];
+        if (D != nullptr) { // C = alpha A B + beta D (D may alias C: read, then written, here)
+          const BVec<T, VEC> dv = load_d<T, VEC>(D + row * ldd + c0);
+#pragma unroll
+          for (int u = 0; u < VEC; ++u)
+            out.v[u] += beta * dv.v[u];
+        }
         store_c<T, VEC>(C + row * ldc + c0, out);
       }
     }
@@ -257,7 +276,7 @@ __global__ void __launch_bounds__(256)
 spmm_combine_kernel(const int64_t* __restrict__ segments,
                     const int64_t num_segments, const T* __restrict__ partial,
                     T* __restrict__ C, const int64_t ldc, const T alpha,
-                    const int64_t k) {
+                    const int64_t k, const T* D, const int64_t ldd, const T beta) {
   const int64_t s = blockIdx.x;
   const int64_t row = segments[3 * s];
   if (s > 0 && segments[3 * (s - 1)] == row)
@@ -266,7 +285,10 @@ spmm_combine_kernel(const int64_t* __restrict__ segments,
     T sum = T(0);
     for (int64_t q = s; q < num_segments && segments[3 * q] == row; ++q)
       sum += partial[q * k + c];
-    C[row * ldc + c] = alpha * sum;
+    T out = alpha * sum;
+    if (D != nullptr)
+      out += beta * D[row * ldd + c];
+    C[row * ldc + c] = out;
   }
 }
 
@@ -430,6 +452,9 @@ struct RingState {
   const unsigned char* Bsrc; // B + this tile's first column + this lane's granule, as bytes
   T* Cl;                     // C + c0
   int64_t ldc;
+  const T* Dl;               // D + c0, or nullptr (beta = 0)
+  int64_t ldd;
+  T beta;
   unsigned ldb_bytes;
   T alpha;
   int64_t rows;
@@ -474,6 +499,11 @@ struct RingState {
 #pragma unroll
       for (int u = 0; u < VEC; ++u)
         out.v[u] = alpha * acc[u];
+      if (Dl != nullptr) {
+#pragma unroll
+        for (int u = 0; u < VEC; ++u)
+          out.v[u] += beta * Dl[row * ldd + u];
+      }
       store_c_stream<T, VEC>(Cl + row * ldc, out);
     }
 #pragma unroll
@@ -561,7 +591,8 @@ spmm_ring_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
                  const T* __restrict__ B, const unsigned ldb_bytes, T* __restrict__ C,
                  const int64_t ldc, const T alpha, const int64_t rows, const int64_t k,
                  const int64_t* __restrict__ starts, int64_t* __restrict__ carry_row,
-                 T* __restrict__ carry_val, const float l2_fraction) {
+                 T* __restrict__ carry_val, const float l2_fraction, const T* D,
+                 const int64_t ldd, const T beta) {
   using State = RingState<T, I, O, LB, GR>;
   using Shape = RingShape<LB, GR>;
   constexpr int VEC = State::VEC;
@@ -589,6 +620,9 @@ spmm_ring_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
   s.active = c0 < k;
   s.Cl = C + (s.active ? c0 : 0);
   s.ldc = ldc;
+  s.Dl = D != nullptr ? D + (s.active ? c0 : 0) : nullptr;
+  s.ldd = ldd;
+  s.beta = beta;
   s.ldb_bytes = ldb_bytes;
   s.alpha = alpha;
   s.rows = rows;
@@ -724,7 +758,9 @@ int launch_spmm_ring(spblas_b200_plan* p, const T alpha, const void* values,
       static_cast<const T*>(values), static_cast<const O*>(p->csr_perm),
       static_cast<const T*>(B), unsigned(ldb * int64_t(sizeof(T))), static_cast<T*>(C), ldc,
       alpha, p->csr_rows, k, static_cast<const int64_t*>(p->spmm_starts.p),
-      static_cast<int64_t*>(p->spmm_carry_row.p), static_cast<T*>(p->spmm_carry_val.p), frac);
+      static_cast<int64_t*>(p->spmm_carry_row.p), static_cast<T*>(p->spmm_carry_val.p), frac,
+      static_cast<const T*>(p->epi_d), p->epi_ldd,
+      p->epi_d ? *reinterpret_cast<const T*>(p->epi_beta) : T(0));
   e = cudaGetLastError();
   if (e != cudaSuccess)
     return cuda_fail(p, e, "spmm_ring_kernel");
@@ -765,7 +801,9 @@ int launch_spmm(spblas_b200_plan* p, const T alpha, const void* values,
       kern<<<grid, kSpmmThreads, 0, p->stream>>>(
           static_cast<const O*>(p->csr_rowptr), static_cast<const I*>(p->csr_colind),
           static_cast<const T*>(values), static_cast<const O*>(p->csr_perm),
-          static_cast<const T*>(B), ldb, static_cast<T*>(C), ldc, alpha, rows, k, seg_limit);
+          static_cast<const T*>(B), ldb, static_cast<T*>(C), ldc, alpha, rows, k, seg_limit,
+          static_cast<const T*>(p->epi_d), p->epi_ldd,
+          p->epi_d ? *reinterpret_cast<const T*>(p->epi_beta) : T(0));
       return cudaGetLastError();
     };
     // three resident CTAs per SM (<= 80 registers) measured best on C3: two lose
@@ -791,7 +829,9 @@ int launch_spmm(spblas_b200_plan* p, const T alpha, const void* values,
       return cuda_fail(p, e, "spmm_segment_kernel");
     spmm_combine_kernel<T><<<unsigned(p->num_segments), 256, 0, p->stream>>>(
         static_cast<const int64_t*>(p->segments.p), p->num_segments,
-        static_cast<const T*>(p->seg_partial.p), static_cast<T*>(C), ldc, alpha, k);
+        static_cast<const T*>(p->seg_partial.p), static_cast<T*>(C), ldc, alpha, k,
+        static_cast<const T*>(p->epi_d), p->epi_ldd,
+        p->epi_d ? *reinterpret_cast<const T*>(p->epi_beta) : T(0));
     e = cudaGetLastError();
     if (e != cudaSuccess)
       return cuda_fail(p, e, "spmm_combine_kernel");
@@ -812,7 +852,8 @@ int spmm_pass(spblas_b200_plan* p, const void* alpha, const void* values,
     return (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
   };
   const bool vec = (k % V == 0) && (ldb % V == 0) && (ldc % V == 0) &&
-                   aligned16(B) && aligned16(C);
+                   aligned16(B) && aligned16(C) &&
+                   (p->epi_d == nullptr || (p->epi_ldd % V == 0 && aligned16(p->epi_d)));
   // Stream kernel when a row of B is at least kRingMinRowBytes long: there it reaches
   // the DRAM peak on its traffic (C3 k=128: 6.4 TB/s), while on 128-byte rows both
   // kernels sit at the same random-access DRAM ceiling (~4.3 TB/s) and the group kernel

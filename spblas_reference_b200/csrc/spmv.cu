@@ -35,6 +35,8 @@
 // tiny kernel adds carries to y in tile order (deterministic, no floating-point
 // atomics).  y is written exactly once per row by the tile that holds the row's
 // end, so beta = 0 semantics (stale y, even NaN, is discarded) hold without a memset.
+#include <algorithm>
+
 #include "device_utils.cuh"
 #include "plan.hpp"
 
@@ -146,7 +148,27 @@ struct ScatterArgs {
   int64_t lo_min, hi_max; // union of the ranges: tiles outside skip all checks
   T* dst[kMaxPeers];
   int64_t lo[kMaxPeers], hi[kMaxPeers];
+  // y = alpha A x + beta d (the 4-argument multiply, spblas_b200_spmv_axpby): the addend is
+  // fused into the one store every row gets; d == nullptr: beta = 0, nothing is read.  d may
+  // alias y (each element is read, then written, by the same thread).  These live in the
+  // kernel's parameter bank: the test is uniform and costs no register in the hot loops.
+  const T* d;
+  T beta;
+  // a call on a cached one-shot structure: run only if the verify kernel that precedes it on
+  // the stream found the structure unchanged (*gate == gate_value); nullptr: no gate
+  const unsigned int* gate;
+  unsigned int gate_value;
 };
+
+template <typename T>
+__device__ __forceinline__ bool gate_closed(const ScatterArgs<T>& sc) {
+  return sc.gate != nullptr && *reinterpret_cast<const volatile unsigned int*>(sc.gate) != sc.gate_value;
+}
+
+template <typename T>
+__device__ __forceinline__ T with_addend(const ScatterArgs<T>& sc, int64_t row, T v) {
+  return sc.d != nullptr ? v + sc.beta * sc.d[row] : v;
+}
 
 struct BarrierArgs {
   int n;
@@ -274,7 +296,7 @@ uniform_rows(const I* __restrict__ col, const T* __restrict__ val,
              const T* __restrict__ x, T* __restrict__ yrow, const T alpha, int e0,
              int nrows, int tid, const ScatterArgs<T>& sc, int64_t rowbase) {
   for (int r = tid; r < nrows; r += CONS) {
-    const T v = alpha * dot_exact<L, T, I>(col, val, x, e0 + L * r);
+    const T v = with_addend(sc, rowbase + r, alpha * dot_exact<L, T, I>(col, val, x, e0 + L * r));
     yrow[r] = v;
     if constexpr (SCAT) // a tile a peer needs rows of (rare: the loop above stays lean)
       scatter_store(sc, rowbase + r, v);
@@ -420,6 +442,8 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const bool has_perm = perm != nullptr;
+  if (gate_closed(sc))
+    return;
 
   // contiguous run of tiles for this CTA out of [tile_first, tile_first + num_tiles)
   const int64_t t_begin = tile_first + num_tiles * int64_t(blockIdx.x) / gridDim.x;
@@ -580,6 +604,7 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
     // does a peer need rows of this tile?
     const bool scat = wants_rows(sc, row0, row0 + nr);
     auto put = [&](int64_t row, T v) {
+      v = with_addend(sc, row, v);
       y[row] = v;
       if (scat)
         scatter_store(sc, row, v);
@@ -792,7 +817,7 @@ __device__ __forceinline__ T ws_gather(const T* p) {
     return ld_ro(p);
 }
 
-template <typename T, typename I, typename O, bool HUB, int WARPS>
+template <typename T, typename I, typename O, int HUB, int WARPS>
 __device__ __forceinline__ void
 ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
                 const T* __restrict__ values, const O* __restrict__ perm,
@@ -801,7 +826,7 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
                 const int64_t num_streams, const int64_t rows, const int64_t nnz_end,
                 int64_t* __restrict__ carry_row, T* __restrict__ carry_val,
                 const ScatterArgs<T>& sc, const int lane, const int warp, T* slab,
-                const uint32_t hub) {
+                const uint32_t hub, const T* __restrict__ xh = nullptr) {
   const int64_t gw = int64_t(blockIdx.x) * WARPS + warp;
   const int64_t nw = int64_t(gridDim.x) * WARPS;
   const bool has_perm = perm != nullptr;
@@ -812,6 +837,7 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
     const int64_t row_e = starts[2 * s + 2];
     const bool scat = wants_rows(sc, row, row_e);
     auto put = [&](int64_t r, T v) {
+      v = with_addend(sc, r, v);
       y[r] = v;
       if (scat)
         scatter_store(sc, r, v);
@@ -865,11 +891,15 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
           T xv[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if constexpr (HUB)
-              xv[j] = c.v[j] < I(0) ? ld_hub<T>(hub, int(~c.v[j]))
-                                    : ws_gather<HUB>(x + c.v[j]);
-            else
-              xv[j] = ws_gather<HUB>(x + c.v[j]);
+            if constexpr (HUB == 1) {
+              xv[j] = c.v[j] < I(0) ? ld_hub<T>(hub, int(~c.v[j])) : ws_gather<true>(x + c.v[j]);
+            } else if constexpr (HUB == 2) {
+              // one load either way: a negative index reads the compact table
+              const bool h = c.v[j] < I(0);
+              xv[j] = ld_ro((h ? xh : x) + (h ? ~c.v[j] : c.v[j]));
+            } else {
+              xv[j] = ws_gather<false>(x + c.v[j]);
+            }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -989,7 +1019,9 @@ spmv_warp_stream_kernel(const O* __restrict__ rowptr, const I* __restrict__ coli
   __shared__ __align__(16) T s_slab[kWsWarps][kWsChunk];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  ws_walk_streams<T, I, O, false, kWsWarps>(rowptr, colind, values, perm, x, y, alpha, starts,
+  if (gate_closed(sc))
+    return;
+  ws_walk_streams<T, I, O, 0, kWsWarps>(rowptr, colind, values, perm, x, y, alpha, starts,
                                             stream_first, num_streams, rows, nnz_end,
                                             carry_row, carry_val, sc, lane, warp, s_slab[warp],
                                             0u);
@@ -1032,9 +1064,52 @@ spmv_hub_stream_kernel(const O* __restrict__ rowptr, const int32_t* __restrict__
   const int warp = threadIdx.x >> 5;
   uint32_t hub_addr = smem_u32(hub);
   asm volatile("" : "+r"(hub_addr)); // one register, not a recomputation at every use
-  ws_walk_streams<T, int32_t, O, true, kHubWarps>(
+  ws_walk_streams<T, int32_t, O, 1, kHubWarps>(
       rowptr, hub_colind, values, perm, x, y, alpha, starts, stream_first, num_streams, rows,
       nnz_end, carry_row, carry_val, sc, lane, warp, slabs + warp * kWsChunk, hub_addr);
+}
+
+// ============================================================================
+// Hub table in GLOBAL memory: for x larger than L2
+// ============================================================================
+// When x does not fit in L2 (C5: R-MAT scale 27, x = 1.07 GB) a gather that misses L2 costs
+// a 32-byte DRAM sector, and ncu shows almost all of them do (profiles/
+// r02_ncu_c5shard_warp_stream.txt: 11.05 GB read for 3.3 GB of A — 0.9 sectors per stored
+// entry): the popular columns are scattered over x, one useful element per 128-byte line,
+// and do not survive in L2.  Here the inspect phase's column analysis (hub.cu) picks the
+// columns referenced at least 3 times, up to half of L2 worth of them, hottest first, and
+// re-encodes colind (hub number s -> ~s) exactly as for the shared-memory table; every
+// product first gathers x at those columns into a compact table (hub_fill_kernel: H gathers
+// instead of one per reference) and the walk then reads a negative index from the table:
+// dense lines that stay in L2, the top of it in L1.  Same arithmetic in the same order as
+// the warp-stream kernel: bit-identical y.  Occupancy and shape are the warp-stream kernel's.
+template <typename T>
+__global__ void __launch_bounds__(256)
+hub_fill_kernel(const T* __restrict__ x, const int32_t* __restrict__ hub_cols, const int64_t h,
+                T* __restrict__ xh) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < h; i += stride)
+    xh[i] = ld_ro(x + ld_stream(hub_cols + i));
+}
+
+template <typename T, typename O>
+__global__ void __launch_bounds__(kWsWarps * 32, ws_ctas_per_sm<T, int32_t>())
+spmv_hubg_stream_kernel(const O* __restrict__ rowptr, const int32_t* __restrict__ hub_colind,
+                        const T* __restrict__ values, const O* __restrict__ perm,
+                        const T* __restrict__ x, T* __restrict__ y, const T alpha,
+                        const int64_t* __restrict__ starts, const int64_t stream_first,
+                        const int64_t num_streams, const int64_t rows,
+                        const int64_t nnz_end,
+                        int64_t* __restrict__ carry_row, T* __restrict__ carry_val,
+                        const __grid_constant__ ScatterArgs<T> sc,
+                        const T* __restrict__ xh) {
+  __shared__ __align__(16) T s_slab[kWsWarps][kWsChunk];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  ws_walk_streams<T, int32_t, O, 2, kWsWarps>(rowptr, hub_colind, values, perm, x, y, alpha,
+                                              starts, stream_first, num_streams, rows, nnz_end,
+                                              carry_row, carry_val, sc, lane, warp, s_slab[warp],
+                                              0u, xh);
 }
 
 // ============================================================================
@@ -1066,6 +1141,8 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
+  if (gate_closed(sc))
+    return;
   const int64_t t = tile_first + blockIdx.x;
   const int64_t row0 = tile_starts[2 * t], k0 = tile_starts[2 * t + 1];
   const int64_t row1 = tile_starts[2 * t + 2], k1 = tile_starts[2 * t + 3];
@@ -1081,6 +1158,7 @@ spmv_merge_tile_kernel(const O* __restrict__ rowptr,
     s_nlong = 0;
   const bool scat = wants_rows(sc, row0, row1);
   auto put = [&](int64_t row, T v) {
+    v = with_addend(sc, row, v);
     y[row] = v;
     if (scat)
       scatter_store(sc, row, v);
@@ -1245,6 +1323,8 @@ spmv_carry_fixup_kernel(const int64_t* __restrict__ carry_row,
                         int64_t fix_hi, int64_t num_tiles, T* __restrict__ y,
                         const T alpha, const __grid_constant__ ScatterArgs<T> sc,
                         const __grid_constant__ BarrierArgs bar) {
+  if (gate_closed(sc))
+    return; // (a gated call is never part of a fused exchange: no barrier to keep)
   const int64_t t = fix_lo + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   bool stored_to_peer = false;
   if (t < fix_hi) {
@@ -1323,6 +1403,10 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
   const int64_t nnz_end = p->base + p->nnz;
 
   ScatterArgs<T> sc;
+  sc.gate = p->gate;
+  sc.gate_value = p->gate_value;
+  sc.d = static_cast<const T*>(p->epi_d);
+  sc.beta = sc.d ? *reinterpret_cast<const T*>(p->epi_beta) : T(0);
   sc.n = p->scatter.n;
   sc.multicast = p->scatter.multicast;
   sc.lo_min = INT64_MAX;
@@ -1352,7 +1436,8 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
   cudaError_t e = cudaSuccess;
   // the carry arrays and the unit count of the active partition
   const bool hub = variant == kVariantHubStream;
-  const bool ws = variant == kVariantWarpStream || hub;
+  const bool hubg = variant == kVariantHubGlobal;
+  const bool ws = variant == kVariantWarpStream || hub || hubg;
   const int64_t units = ws ? p->ws_streams : p->num_tiles;
   const int64_t* d_carry_row =
       static_cast<const int64_t*>(ws ? p->ws_carry_row.p : p->carry_row.p);
@@ -1392,6 +1477,48 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
       e = cudaGetLastError();
       if (e != cudaSuccess)
         return cuda_fail(p, e, "spmv_hub_stream_kernel");
+    } else {
+      return fail(p, SPBLAS_B200_NOT_SUPPORTED, "hub variant needs int32 column indices");
+    }
+  } else if (ntiles > 0 && hubg) {
+    if constexpr (sizeof(I) == 4) {
+      // x at the hub columns -> the compact table, then the walk
+      const int64_t h = p->hub_count;
+      if (h > 0) {
+        const unsigned fgrid =
+            unsigned(std::min<int64_t>((h + 255) / 256, int64_t(p->num_sms) * 8));
+        hub_fill_kernel<T><<<fgrid, 256, 0, p->stream>>>(
+            static_cast<const T*>(x), static_cast<const int32_t*>(p->hub_cols.p), h,
+            static_cast<T*>(p->hub_x.p));
+        e = cudaGetLastError();
+        if (e != cudaSuccess)
+          return cuda_fail(p, e, "hub_fill_kernel");
+        p->last_launches += 1;
+        p->total_launches += 1;
+      }
+      int64_t grid = (ntiles + kWsWarps - 1) / kWsWarps;
+      if (grid > int64_t(p->num_sms) * ws_ctas_per_sm<T, I>())
+        grid = int64_t(p->num_sms) * ws_ctas_per_sm<T, I>();
+      int carve = p->ws_carveout;
+      if (carve < 0) {
+        const size_t need =
+            size_t(ws_ctas_per_sm<T, I>()) * (kWsWarps * kWsChunk * sizeof(T) + 1024);
+        carve = int((need * 100 + p->smem_per_sm - 1) / p->smem_per_sm);
+        carve = carve > 100 ? 100 : carve;
+      }
+      auto kern = spmv_hubg_stream_kernel<T, O>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      const int32_t* enc =
+          static_cast<const int32_t*>(p->hub_colind.p) - (p->base & ~int64_t(3));
+      kern<<<unsigned(grid), kWsWarps * 32, 0, p->stream>>>(
+          static_cast<const O*>(p->csr_rowptr), enc, static_cast<const T*>(values),
+          static_cast<const O*>(p->csr_perm), static_cast<const T*>(x), static_cast<T*>(y), a,
+          static_cast<const int64_t*>(p->ws_starts.p), T0, ntiles, p->csr_rows, nnz_end,
+          static_cast<int64_t*>(p->ws_carry_row.p), static_cast<T*>(p->ws_carry_val.p), sc,
+          static_cast<const T*>(p->hub_x.p));
+      e = cudaGetLastError();
+      if (e != cudaSuccess)
+        return cuda_fail(p, e, "spmv_hubg_stream_kernel");
     } else {
       return fail(p, SPBLAS_B200_NOT_SUPPORTED, "hub variant needs int32 column indices");
     }
@@ -1528,21 +1655,29 @@ int prepare_spmv(spblas_b200_plan* p, int val_type, const void* values, int* var
   // the hub variant is offered to matrices that would take the warp-stream kernel, on
   // request (spblas_b200_plan_set_hub / SPBLAS_B200_HUB=1), for inspected plans only: the
   // no-info overloads re-derive the structure on every call and cannot pay for the analysis
+  // ... with the table in shared memory while x fits in L2 (the bound is the L1 port), in
+  // global memory when it does not (the bound is DRAM sectors)
   if (!forced && v == kVariantWarpStream && p->hub_enable && !p->light_inspect)
-    v = kVariantHubStream;
+    v = double(p->csr_cols) * double(type_size_val(val_type)) > 0.75 * double(p->l2_bytes)
+            ? kVariantHubGlobal
+            : kVariantHubStream;
   if (!spmv_vec_ok(p, values))
     v = kVariantMergeTile;
   if (v != kVariantMergeTile && v != kVariantPipelined && v != kVariantWarpStream &&
-      v != kVariantHubStream)
+      v != kVariantHubStream && v != kVariantHubGlobal)
     v = kVariantMergeTile;
-  if (v == kVariantHubStream && (p->idx_type != SPBLAS_B200_I32 || p->host_exec_active))
+  if ((v == kVariantHubStream || v == kVariantHubGlobal) &&
+      (p->idx_type != SPBLAS_B200_I32 || p->host_exec_active))
     v = kVariantWarpStream; // a negative index marks a hub; chunked launches reload the table
   if (p->num_tiles > int64_t(0x7fffffff))
     return fail(p, SPBLAS_B200_NOT_SUPPORTED, "too many tiles for one launch");
-  if (v == kVariantHubStream) {
-    const int64_t cap = hub_capacity(p, type_size_val(val_type), kHubWarps);
-    if (p->hub_state == 0 || (p->hub_state == 1 && p->hub_cap != cap)) {
-      if (int rc = build_hub_table(p, cap))
+  if (v == kVariantHubStream || v == kVariantHubGlobal) {
+    const bool global = v == kVariantHubGlobal;
+    const int64_t cap = global ? hub_global_capacity(p, type_size_val(val_type))
+                               : hub_capacity(p, type_size_val(val_type), kHubWarps);
+    if (p->hub_state == 0 ||
+        (p->hub_state == 1 && (p->hub_cap != cap || p->hub_by_popularity != global))) {
+      if (int rc = build_hub_table(p, cap, global))
         return rc;
       // not worth a CTA-wide table unless a fair share of the gathers leaves the L2 port
       if (!forced && 20 * p->hub_refs < 3 * p->nnz) {
@@ -1553,8 +1688,12 @@ int prepare_spmv(spblas_b200_plan* p, int val_type, const void* values, int* var
     }
     if (p->hub_state != 1)
       v = kVariantWarpStream;
+    else if (global)
+      if (int rc = reserve(p, p->hub_x,
+                           size_t(std::max<int64_t>(p->hub_count, 1)) * type_size_val(val_type)))
+        return rc;
   }
-  const bool ws = v == kVariantWarpStream || v == kVariantHubStream;
+  const bool ws = v == kVariantWarpStream || v == kVariantHubStream || v == kVariantHubGlobal;
   if (ws && p->ws_streams < 0) {
     const bool wide = type_size_val(val_type) == 8 || p->idx_type == SPBLAS_B200_I64;
     const int64_t resident =

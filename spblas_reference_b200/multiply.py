@@ -138,8 +138,8 @@ class operation_info_t:
         _cabi.raise_for_status(st, self._err())
 
     def force_spmv_variant(self, variant: int):
-        """Tuning / test knob: 0 merge-tile, 1 pipelined, 2 warp-stream, 3 hub-stream,
-        -1 automatic (spblas_b200_plan_force_variant)."""
+        """Tuning / test knob: 0 merge-tile, 1 pipelined, 2 warp-stream, 3 hub table in shared
+        memory, 4 hub table in global memory, -1 automatic (spblas_b200_plan_force_variant)."""
         st = _cabi.lib().spblas_b200_plan_force_variant(self._plan, int(variant))
         _cabi.raise_for_status(st, self._err())
 
@@ -265,7 +265,25 @@ def multiply_inspect(*args):
     raise TypeError("multiply_inspect(a, x, y) or multiply_inspect(info, a, x, y)")
 
 
-def _execute(info: Optional[operation_info_t], a, x, y):
+def _decode_addend(d, y, vt):
+    """The 4-argument form's d (vendor/rocsparse/multiply_spgemm.hpp:69-118 convention):
+    beta = scaling factor of d (1 if none); d has y's shape and type; it may BE y."""
+    if is_conjugated(d):
+        raise RuntimeError("b200 backend does not support conjugated views.")
+    d_base = get_ultimate_base(d)
+    if not isinstance(d_base, torch.Tensor) or not d_base.is_cuda:
+        raise RuntimeError("d must live in device memory (no CPU path)")
+    if tuple(d_base.shape) != tuple(y.shape):
+        raise ValueError("multiply: matrix and vector dimensions are incompatible."
+                         if not _is_matrix(y) else "multiply: matrix dimensions are incompatible.")
+    if d_base.dtype != y.dtype:
+        raise RuntimeError("b200 backend needs A, x, y and d of one scalar type")
+    beta = get_scaling_factor(d)
+    beta_np = np.array([1 if beta is None else beta], dtype=_NP[vt])
+    return d_base, beta_np
+
+
+def _execute(info: Optional[operation_info_t], a, x, y, d=None):
     a_base, fmt, ptr, ind = _decode_matrix(a)
     if is_conjugated(x) or is_conjugated(y):
         raise RuntimeError("b200 backend does not support conjugated views.")
@@ -285,25 +303,39 @@ def _execute(info: Optional[operation_info_t], a, x, y):
     dev = a_base.values.device
     L = _cabi.lib()
     m, n = a_base.shape
+    d_base = beta_np = beta_p = None
+    if d is not None:
+        d_base, beta_np = _decode_addend(d, y, vt)
+        beta_p = beta_np.ctypes.data_as(C.c_void_p)
 
     with torch.cuda.device(dev):
         stream = _stream_ptr(dev)
         if info is None:
-            # no operation_info_t: one-shot entry points (thread-local cached plan,
-            # light re-inspect every call)
+            # no operation_info_t: one-shot entry points (thread-local plan; a structure seen
+            # before is reused after a device-side check of its offsets array)
             if _is_matrix(y):
-                st = L.spblas_b200_spmm_once(
-                    stream, fmt, m, n, a_base.nnz, ptr.data_ptr(), ind.data_ptr(),
-                    index_type(ptr), index_type(ind), vt, alpha_p, a_base.values.data_ptr(),
-                    x_base.data_ptr(), _row_major(x_base, "B"), y.data_ptr(),
-                    _row_major(y, "C"), int(y.shape[1]))
+                common = (stream, fmt, m, n, a_base.nnz, ptr.data_ptr(), ind.data_ptr(),
+                          index_type(ptr), index_type(ind), vt, alpha_p, a_base.values.data_ptr(),
+                          x_base.data_ptr(), _row_major(x_base, "B"))
+                if d is None:
+                    st = L.spblas_b200_spmm_once(*common, y.data_ptr(), _row_major(y, "C"),
+                                                 int(y.shape[1]))
+                else:
+                    st = L.spblas_b200_spmm_axpby_once(*common, beta_p, d_base.data_ptr(),
+                                                       _row_major(d_base, "D"), y.data_ptr(),
+                                                       _row_major(y, "C"), int(y.shape[1]))
             else:
                 _check_1d_cuda(x_base, "x")
                 _check_1d_cuda(y, "y")
-                st = L.spblas_b200_spmv_once(
-                    stream, fmt, m, n, a_base.nnz, ptr.data_ptr(), ind.data_ptr(),
-                    index_type(ptr), index_type(ind), vt, alpha_p, a_base.values.data_ptr(),
-                    x_base.data_ptr(), y.data_ptr())
+                common = (stream, fmt, m, n, a_base.nnz, ptr.data_ptr(), ind.data_ptr(),
+                          index_type(ptr), index_type(ind), vt, alpha_p, a_base.values.data_ptr(),
+                          x_base.data_ptr())
+                if d is None:
+                    st = L.spblas_b200_spmv_once(*common, y.data_ptr())
+                else:
+                    _check_1d_cuda(d_base, "d")
+                    st = L.spblas_b200_spmv_axpby_once(*common, beta_p, d_base.data_ptr(),
+                                                       y.data_ptr())
             _cabi.raise_for_status(st, L.spblas_b200_last_error_once().decode())
             return
 
@@ -314,33 +346,51 @@ def _execute(info: Optional[operation_info_t], a, x, y):
         plan = info._plan
         L.spblas_b200_plan_set_stream(plan, stream)
         if _is_matrix(y):
-            st = L.spblas_b200_spmm(plan, vt, alpha_p, a_base.values.data_ptr(),
-                                    x_base.data_ptr(), _row_major(x_base, "B"), y.data_ptr(),
-                                    _row_major(y, "C"), int(y.shape[1]))
+            if d is None:
+                st = L.spblas_b200_spmm(plan, vt, alpha_p, a_base.values.data_ptr(),
+                                        x_base.data_ptr(), _row_major(x_base, "B"), y.data_ptr(),
+                                        _row_major(y, "C"), int(y.shape[1]))
+            else:
+                st = L.spblas_b200_spmm_axpby(plan, vt, alpha_p, a_base.values.data_ptr(),
+                                              x_base.data_ptr(), _row_major(x_base, "B"), beta_p,
+                                              d_base.data_ptr(), _row_major(d_base, "D"),
+                                              y.data_ptr(), _row_major(y, "C"), int(y.shape[1]))
         else:
             _check_1d_cuda(x_base, "x")
             _check_1d_cuda(y, "y")
-            st = L.spblas_b200_spmv(plan, vt, alpha_p, a_base.values.data_ptr(),
-                                    x_base.data_ptr(), y.data_ptr())
+            if d is None:
+                st = L.spblas_b200_spmv(plan, vt, alpha_p, a_base.values.data_ptr(),
+                                        x_base.data_ptr(), y.data_ptr())
+            else:
+                _check_1d_cuda(d_base, "d")
+                st = L.spblas_b200_spmv_axpby(plan, vt, alpha_p, a_base.values.data_ptr(),
+                                              x_base.data_ptr(), beta_p, d_base.data_ptr(),
+                                              y.data_ptr())
         _cabi.raise_for_status(st, info._err())
 
 
 def multiply(*args):
     """multiply(a, x, y) or multiply(info, a, x, y): y = alpha * A * x (SpMV) or
-    C = alpha * A * B (SpMM, row-major 2-D tensors); y / C is overwritten (beta = 0)."""
-    if len(args) == 3:
+    C = alpha * A * B (SpMM, row-major 2-D tensors); y / C is overwritten (beta = 0).
+    multiply(a, x, y, d) or multiply(info, a, x, y, d): the 4-argument form sketched in the
+    reference's notes/matrices.hpp and implemented there for rocSPARSE SpGEMM
+    (vendor/rocsparse/multiply_spgemm.hpp:69-118): y = alpha * A * x + beta * d with
+    beta = the scaling factor of d (multiply(a, x, y, scaled(beta, d)); 1 if d is not scaled);
+    d may be y itself.  The addend is fused into the kernels' single store per row."""
+    if args and isinstance(args[0], operation_info_t):
+        if len(args) in (4, 5):
+            return _execute(*args)
+    elif len(args) in (3, 4):
         return _execute(None, *args)
-    if len(args) == 4 and isinstance(args[0], operation_info_t):
-        return _execute(*args)
-    raise TypeError("multiply(a, x, y) or multiply(info, a, x, y)")
+    raise TypeError("multiply(a, x, y[, d]) or multiply(info, a, x, y[, d])")
 
 
-def multiply_execute(info: operation_info_t, a, x, y):
+def multiply_execute(info: operation_info_t, a, x, y, d=None):
     """The execute phase under the name the reference documents (README.md:46,
-    notes/spmv.hpp:20-22); identical to multiply(info, a, x, y)."""
+    notes/spmv.hpp:20-22); identical to multiply(info, a, x, y[, d])."""
     if not isinstance(info, operation_info_t):
-        raise TypeError("multiply_execute(info, a, x, y)")
-    return _execute(info, a, x, y)
+        raise TypeError("multiply_execute(info, a, x, y[, d])")
+    return _execute(info, a, x, y, d)
 
 
 def multiply_execute_host(info: operation_info_t, a, x_host: torch.Tensor, y_host: torch.Tensor):

@@ -185,6 +185,35 @@ void spmv_cases() {
       expect_all_close(host_spmv<T, I, O>(m, rowptr, colind, values, x, T(2)), y_host);
     }
 
+    g_case = "SpMV 4-argument form: y = alpha A x + beta d";
+    {
+      std::vector<T> d(m);
+      for (int i = 0; i < m; ++i)
+        d[i] = T(1 + i % 5);
+      device_array<T> d_d(d);
+      std::span<T> d_span(d_d.get(), m);
+      auto expect = [&](T alpha, T beta, const std::vector<T>& dd) {
+        std::vector<T> r = host_spmv<T, I, O>(m, rowptr, colind, values, x, alpha);
+        for (int i = 0; i < m; ++i)
+          r[i] += beta * dd[i];
+        return r;
+      };
+      spblas::multiply(a, x_span, y_span, d_span);                        // beta = 1, no info
+      expect_all_close(expect(T(1), T(1), d), d_y.to_host());
+      spblas::multiply(moved, spblas::scaled(2.0f, a), x_span, y_span,
+                       spblas::scaled(-3.0f, d_span));                     // alpha = 2, beta = -3
+      expect_all_close(expect(T(2), T(-3), d), d_y.to_host());
+      spblas::multiply_execute(moved, a, x_span, y_span, spblas::scaled(0.5f, d_span));
+      expect_all_close(expect(T(1), T(0.5), d), d_y.to_host());
+      // in place: y = A x + 2 y (the solver update)
+      CUDA_OK(cudaMemcpy(d_y.get(), d.data(), m * sizeof(T), cudaMemcpyHostToDevice));
+      spblas::multiply(moved, a, x_span, y_span, spblas::scaled(2.0f, y_span));
+      expect_all_close(expect(T(1), T(2), d), d_y.to_host());
+      // a second no-info call on the same structure: the cached plan, checked on the device
+      spblas::multiply(a, x_span, y_span, spblas::scaled(2.0f, d_span));
+      expect_all_close(expect(T(1), T(2), d), d_y.to_host());
+    }
+
     g_case = "SpMV matrix_opt";
     spblas::matrix_opt a_opt(a);
     auto info2 = spblas::multiply_inspect(a_opt, x_span, y_span);
@@ -277,6 +306,27 @@ void spmm_cases() {
       spblas::multiply_execute(info, a_opt, b, c);
       expect_all_close(host_spmm<T, I, I>(m, n, rowptr, colind, values, b_values, T(1)),
                        d_c.to_host());
+      g_case = "SpMM 4-argument form n=" + std::to_string(n);
+      {
+        std::vector<T> dd(std::size_t(m) * n);
+        for (std::size_t i = 0; i < dd.size(); ++i)
+          dd[i] = T(1 + i % 7);
+        device_array<T> d_d(dd);
+        spblas::mdspan_row_major<T, I> d(d_d.get(), m, n);
+        auto expect = [&](T alpha, T beta) {
+          std::vector<T> r = host_spmm<T, I, I>(m, n, rowptr, colind, values, b_values, alpha);
+          for (std::size_t i = 0; i < r.size(); ++i)
+            r[i] += beta * dd[i];
+          return r;
+        };
+        spblas::multiply(a, b, c, d);
+        expect_all_close(expect(T(1), T(1)), d_c.to_host());
+        spblas::multiply(info, spblas::scaled(2.0f, a_opt), b, c, spblas::scaled(-1.5f, d));
+        expect_all_close(expect(T(2), T(-1.5)), d_c.to_host());
+        CUDA_OK(cudaMemcpy(d_c.get(), dd.data(), dd.size() * sizeof(T), cudaMemcpyHostToDevice));
+        spblas::multiply_execute(info, a_opt, b, c, spblas::scaled(3.0f, c)); // in place
+        expect_all_close(expect(T(1), T(3)), d_c.to_host());
+      }
     }
   }
 }

@@ -94,6 +94,56 @@ def test_hub_structures_and_product(cuda, oracle, kind, types):
     i_hub.close()
 
 
+@pytest.mark.parametrize("kind", ["short", "hubrow", "long"])
+@pytest.mark.parametrize("types", [(np.float32, np.int32), (np.float64, np.int64), (np.int32, np.int32)])
+def test_global_hub_table_structures_and_product(cuda, oracle, kind, types):
+    """Variant 4: the hub table in global memory, hottest column first (for x larger than L2).
+    Table, encoded colind and reference count against the oracle's definition; y bit-identical
+    to the warp-stream kernel's."""
+    vt, ot = types
+    rng = np.random.default_rng(zlib.crc32(f"hubg{kind}{vt.__name__}{ot.__name__}".encode()))
+    m, n = 6007, 4099
+    v, rp, ci, x = _skewed_csr(rng, m, n, _lens(rng, m, kind), vt, ot)
+    a = csr_on_device(v, rp, ci, (m, n))
+    xd = dev(x)
+    alpha = 3 if vt == np.int32 else 0.75
+    y_ws, i_ws = _run(a, xd, m, 2, alpha=alpha)
+    y_hub, i_hub = _run(a, xd, m, 4, hub=(300, 3), alpha=alpha)
+    hubs, refs, enc = oracle.hub_columns(ci, n, 300, 3, by_popularity=True)
+    assert i_hub.spmv_variant == 4
+    assert i_hub.hub_count == len(hubs) and i_hub.hub_refs == refs
+    assert np.array_equal(i_hub.hub_cols, hubs)
+    assert np.array_equal(i_hub.hub_colind, enc)
+    assert torch.equal(y_ws, y_hub)
+    y_ref = oracle.spmv("csr", (m, n), rp, ci, v, x, alpha_a=alpha)
+    bound = None if vt == np.int32 else oracle.abs_rowsum(rp, ci, v, x, alpha)
+    assert_rows_within_bound(y_hub.cpu().numpy(), y_ref, rp, bound, f"global hub {kind}")
+    # a second product with another x: the table is refilled by every product
+    x2 = dev((x * 2).astype(vt))
+    y2 = torch.empty_like(y_hub)
+    sb.multiply_execute(i_hub, sb.scaled(alpha, a), x2, y2)
+    y2_ws = torch.empty_like(y_hub)
+    sb.multiply_execute(i_ws, sb.scaled(alpha, a), x2, y2_ws)
+    assert torch.equal(y2, y2_ws)
+    i_ws.close()
+    i_hub.close()
+
+
+def test_global_hub_table_is_not_chosen_for_a_small_x(cuda, oracle):
+    """matrix_opt picks the global table only when x exceeds 3/4 of L2; a small x keeps the
+    shared-memory table or the plain walk."""
+    rng = np.random.default_rng(5)
+    m, n = 4001, 3001
+    v, rp, ci, x = _skewed_csr(rng, m, n, _lens(rng, m, "hubrow"), np.float64)
+    a = sb.matrix_opt(csr_on_device(v, rp, ci, (m, n)))
+    xd = dev(x)
+    y = torch.empty(m, dtype=torch.float64, device="cuda")
+    info = sb.multiply_inspect(a, xd, y)
+    sb.multiply_execute(info, a, xd, y)
+    assert info.spmv_variant in (2, 3)
+    info.close()
+
+
 @pytest.mark.parametrize("r0", [777, 778, 779, 780])
 def test_hub_on_a_row_block_with_an_unaligned_base(cuda, oracle, r0):
     """A shard keeps the global rowptr base; rp[r0] % 4 takes every value over the four
@@ -277,7 +327,7 @@ def test_hub_rmat_reduced(cuda, oracle, monkeypatch):
     i_hub.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_fuzz_spmv_kernels_on_arbitrary_small_structures(cuda, oracle, variant):
     """Property test (hypothesis): every SpMV kernel on arbitrary small structures — no rows,
     empty rows, one very long row, duplicates, a row block with a non-zero base — integer
@@ -299,14 +349,14 @@ def test_fuzz_spmv_kernels_on_arbitrary_small_structures(cuda, oracle, variant):
         x = rng.integers(-9, 10, size=n).astype(np.int32)
         a = csr_on_device(v, rp, ci, (m, n))
         xd = dev(x)
-        y, info = _run(a, xd, m, variant, hub=(16, 1) if variant == 3 else None, alpha=2)
+        y, info = _run(a, xd, m, variant, hub=(16, 1) if variant >= 3 else None, alpha=2)
         assert np.array_equal(y.cpu().numpy(), oracle.spmv("csr", (m, n), rp, ci, v, x, alpha_a=2))
         info.close()
         if m >= 4:                                   # rows [r0, r1) with the global base
             r0, r1 = m // 4, m - m // 4
             blk = sb.csr_view(a.values, a.rowptr[r0:r1 + 1], a.colind, (r1 - r0, n),
                               int(rp[r1] - rp[r0]))
-            yb, ib = _run(blk, xd, r1 - r0, variant, hub=(16, 1) if variant == 3 else None)
+            yb, ib = _run(blk, xd, r1 - r0, variant, hub=(16, 1) if variant >= 3 else None)
             assert np.array_equal(yb.cpu().numpy(), oracle.spmv("csr", (m, n), rp, ci, v, x)[r0:r1])
             ib.close()
 
