@@ -319,6 +319,8 @@ def main():
     # x0 = U[0,1) (splitmix64, seed 1: SURVEY 8d's variant).  With x0 = 1 the iterate is 0 on
     # every interior row from the second step on, and the timed loop would multiply zeros.
     x0 = G.dense_uniform((n,), 1, torch.float64, dev)
+    if os.environ.get("SPBLAS_B200_BENCH_X0") == "ones":     # round 1's operand, for A/B runs only
+        x0.fill_(1.0)
     info = sb.multiply_inspect(a, x0, torch.empty(m_loc, dtype=torch.float64, device=dev))
     t_ins0 = time.perf_counter()
     sb.multiply_inspect(info, a, x0, torch.empty(m_loc, dtype=torch.float64, device=dev))

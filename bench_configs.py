@@ -192,7 +192,7 @@ def roofline(nbytes, ms, peak, peak_src, traffic, kernel):
 
 
 SPMV_KERNEL = {0: "spmv_merge_tile_kernel", 1: "spmv_pipe_kernel", 2: "spmv_warp_stream_kernel",
-               3: "spmv_hub_stream_kernel"}
+               3: "spmv_hub_stream_kernel", 4: "spmv_hubg_stream_kernel"}
 
 
 def _free(*names):
@@ -364,14 +364,30 @@ def config_c5(ctx, scale=27, with_spmm=True):
     gen_s = time.perf_counter() - t0
     m_loc, nnz_loc = shape[0], int(ci.numel())
     r0, r1 = blocks[rank]
-    a = sb.csr_view(v, rp, ci, shape, nnz_loc)
+    a_plain = sb.csr_view(v, rp, ci, shape, nnz_loc)
+    # matrix_opt: the reference's marker for "the backend may keep optimised state for this
+    # matrix" — here x at the most referenced columns in a compact table (x is 1.07 GB at scale
+    # 27: a gather that misses L2 costs a DRAM sector)
+    a = sb.matrix_opt(a_plain) if os.environ.get("SPBLAS_B200_MATRIX_OPT", "1") != "0" else a_plain
     alpha = 1.0 / max_deg                       # keeps the iterates in [0, 1]
     a_scaled = sb.scaled(alpha, a)
     x0 = G.dense_uniform((n,), 5, torch.float64, dev)
     t0 = time.perf_counter()
-    info = sb.multiply_inspect(a, x0, torch.empty(m_loc, dtype=torch.float64, device=dev))
+    y_tmp = torch.empty(m_loc, dtype=torch.float64, device=dev)
+    info = sb.multiply_inspect(a, x0, y_tmp)
     torch.cuda.synchronize()
     inspect_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    sb.multiply_execute(info, a_scaled, x0, y_tmp)      # first product: builds the lazy tables
+    torch.cuda.synchronize()
+    first_ms = (time.perf_counter() - t0) * 1e3
+    # the plain operand (no matrix_opt) beside it: kernel only
+    info_plain = sb.multiply_inspect(a_plain, x0, y_tmp)
+    plain_ms = max_over_ranks(time_loop(
+        lambda i: sb.multiply_execute(info_plain, sb.scaled(alpha, a_plain), x0, y_tmp), 5, 2))
+    plain_variant = info_plain.spmv_variant
+    info_plain.close()
+    del y_tmp
     op = ShardedSpMV(n, blocks, (0, n), lambda x, y: sb.multiply_execute(info, a_scaled, x, y),
                      torch.float64, dev, info=info,
                      fused=None if os.environ.get("SPBLAS_B200_FUSED", "1") != "0" else False,
@@ -453,8 +469,12 @@ def config_c5(ctx, scale=27, with_spmm=True):
           "rows_rank0": m_loc if rank == 0 else None, "nnz_rank0": nnz_loc if rank == 0 else None,
           "ms": step_ms, "gflops": flops / step_ms / 1e6, "steps": Kc,
           "kernel_only_ms": kern_ms, "kernel_only_gflops": flops / kern_ms / 1e6,
-          "generate_s": gen_s, "inspect_ms": inspect_ms, "max_row_len": info.max_row_len,
+          "generate_s": gen_s, "inspect_ms": inspect_ms, "first_execute_ms": first_ms,
+          "max_row_len": info.max_row_len,
           "spmv_variant": info.spmv_variant, "gpu_launches": launches,
+          "hub_columns": info.hub_count, "hub_reference_share": info.hub_refs / max(nnz_loc, 1),
+          "plain_operand": {"kernel_only_ms": plain_ms, "spmv_variant": plain_variant,
+                            "what": "the same product without matrix_opt (warp-stream kernel)"},
           "exchange": {"mode": op.plan.mode,
                        "impl": op.exchange_impl, "calibration": op.calibration,
                        "bytes_received_per_gpu_per_step": exchange_bytes if world > 1 else 0,
@@ -463,7 +483,8 @@ def config_c5(ctx, scale=27, with_spmm=True):
           "l2_policy": "inputs larger than L2",
           "roofline": roofline(nbytes, kern_ms, ctx["peak"], ctx["peak_src"],
                                ctx["traffic"](f"c5_n{world}"),
-                               SPMV_KERNEL.get(info.spmv_variant, "?") + "<double,int,long>"),
+                               SPMV_KERNEL.get(info.spmv_variant, "?") + "<double,int,long>"
+                               + (" (+ hub_fill_kernel)" if info.spmv_variant == 4 else "")),
           "cpu_baseline": cpu if rank == 0 else None, "e2e": e2e, "parity": parity}
     c5["roofline"]["note"] = ("per GPU: this rank-0-timed launch streams its block of A and gathers "
                               "from the full replicated x (1.07 GB at scale 27: beyond L2, so a gather "
@@ -479,6 +500,7 @@ def config_c5(ctx, scale=27, with_spmm=True):
     torch.cuda.empty_cache()
     B = G.dense_uniform_rows(n, k, 6, torch.float64, dev)
     C = torch.empty((m_loc, k), dtype=torch.float64, device=dev)
+    a = a_plain
     info_mm = sb.multiply_inspect(a, B, C)
     Km = max(2, min(K, 4))
     for i in range(2):

@@ -104,7 +104,7 @@ def run_spmv(wl, reps):
         sb.multiply_execute(info, a, x, y)
     ms = timed(fn, reps)
     a, x, y, info = ops[0]
-    nnz = a.nnz
+    nnz = int(sets[0][2].numel())
     sT = v.element_size()
     nbytes = nnz * (sT + 4) + (shape[0] + 1) * rp.element_size() + shape[1] * sT + shape[0] * sT
     print(json.dumps({"exp": "spmv", "workload": wl, "lib": os.path.basename(_cabi.LIB_PATH),

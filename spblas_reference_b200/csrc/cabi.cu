@@ -84,6 +84,9 @@ void release_all(spblas_b200_plan* p) {
   release_host_exec(p);
   release_trsv_graphs(p);
   release(p->trsv_params);
+  if (p->trsv_done_event)
+    cudaEventDestroy(p->trsv_done_event);
+  p->trsv_done_event = nullptr;
   if (p->trsv_capture_stream)
     cudaStreamDestroy(p->trsv_capture_stream);
   p->trsv_capture_stream = nullptr;
@@ -136,16 +139,28 @@ struct OnceKey {
            n == o.n && nnz == o.nnz && ptr == o.ptr && ind == o.ind;
   }
 };
-struct OncePlanHolder {
+constexpr int kOnceEntries = 8; // structures a thread's one-shot cache keeps (LRU)
+struct OnceEntry {
   spblas_b200_plan* plan = nullptr;
   bool cached = false; // plan holds the light-inspected structure of `key`
   OnceKey key;
+  unsigned long long last_use = 0;
+};
+struct OncePlanHolder {
+  std::vector<OnceEntry> entries;
+  unsigned long long clock = 0;
+  void release_all_entries() {
+    for (OnceEntry& e : entries)
+      if (e.plan)
+        spblas_b200_plan_destroy(e.plan);
+    entries.clear();
+  }
   ~OncePlanHolder() {
     // Thread exit: give the device buffers back while the runtime is still there (at process
     // exit it may already be unloading: then the context takes everything with it).
-    if (plan && cudaFree(nullptr) == cudaSuccess)
-      spblas_b200_plan_destroy(plan);
-    plan = nullptr;
+    if (!entries.empty() && cudaFree(nullptr) == cudaSuccess)
+      release_all_entries();
+    entries.clear();
   }
 };
 thread_local OncePlanHolder g_once;
@@ -220,8 +235,6 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     p->stages = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_CTAS_PER_SM"))
     p->ctas_per_sm = std::atoi(v);
-  if (const char* v = std::getenv("SPBLAS_B200_CONSUMER_WARPS"))
-    p->consumer_warps = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_WS_ITEMS")) {
     const int t = std::atoi(v);
     if (t >= 256 && t <= (1 << 20))
@@ -365,6 +378,13 @@ int spblas_b200_inspect(spblas_b200_plan* p, int format, int64_t m, int64_t n,
   NvtxRange nvtx_range("spblas_b200_inspect");
   p->err.clear();
   p->inspected = false;
+  // the plan is about to describe a product: a triangular structure it held shares the
+  // index types and the owned buffers, and must not survive (trsv after this needs its own
+  // trsv_inspect)
+  if (p->trsv_ready) {
+    p->trsv_ready = false;
+    release_trsv_graphs(p);
+  }
   p->host_chunks = 0; // the chunk table belongs to the previous structure
   p->cached_values = false;
   p->hub_state = 0; // so does the hub table
@@ -632,28 +652,46 @@ int spblas_b200_spmm(spblas_b200_plan* p, int val_type, const void* alpha,
   return run_spmm(p, val_type, alpha, d_values, d_B, ldb, d_C, ldc, k);
 }
 
-static int once_plan(void* stream, spblas_b200_plan** out) {
-  if (!g_once.plan) {
-    int rc = spblas_b200_plan_create(&g_once.plan, stream);
-    if (rc) {
-      g_once_error = "could not create the one-shot plan";
-      return rc;
-    }
-  }
+// The entry of the calling thread's cache for `key`: the one that holds it (a hit: *out_entry
+// ->cached stays true), else a free or the least recently used one (its plan's buffers are
+// reused for the new structure).
+static int once_plan(void* stream, const OnceKey& key, OnceEntry** out_entry) {
   int dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess && dev != g_once.plan->device) {
-    // buffers belong to another device: start over on this one
-    spblas_b200_plan_destroy(g_once.plan);
-    g_once.plan = nullptr;
-    g_once.cached = false;
-    int rc = spblas_b200_plan_create(&g_once.plan, stream);
+  cudaGetDevice(&dev);
+  OnceEntry* pick = nullptr;
+  for (OnceEntry& e : g_once.entries) {
+    if (e.plan && e.plan->device != dev)
+      continue; // buffers of another device
+    if (e.cached && e.key == key) {
+      pick = &e;
+      break;
+    }
+  }
+  if (!pick) {
+    if (int(g_once.entries.size()) < kOnceEntries) {
+      g_once.entries.emplace_back();
+      pick = &g_once.entries.back();
+    } else {
+      for (OnceEntry& e : g_once.entries)
+        if (!pick || e.last_use < pick->last_use)
+          pick = &e;
+      pick->cached = false;
+      if (pick->plan && pick->plan->device != dev) {
+        spblas_b200_plan_destroy(pick->plan);
+        pick->plan = nullptr;
+      }
+    }
+  }
+  if (!pick->plan) {
+    const int rc = spblas_b200_plan_create(&pick->plan, stream);
     if (rc) {
       g_once_error = "could not create the one-shot plan";
       return rc;
     }
   }
-  g_once.plan->stream = static_cast<cudaStream_t>(stream);
-  *out = g_once.plan;
+  pick->last_use = ++g_once.clock;
+  pick->plan->stream = static_cast<cudaStream_t>(stream);
+  *out_entry = pick;
   return SPBLAS_B200_SUCCESS;
 }
 
@@ -680,22 +718,23 @@ static int spmv_once_impl(void* stream, int format, int64_t m, int64_t n, int64_
                           int val_type, const void* alpha, const void* d_values,
                           const void* d_x, const void* beta, const void* d_d, void* d_y) {
   g_once_error.clear();
-  spblas_b200_plan* p = nullptr;
-  int rc = once_plan(stream, &p);
+  OnceKey key;
+  key.format = format, key.off_type = off_type, key.idx_type = idx_type;
+  key.m = m, key.n = n, key.nnz = nnz, key.ptr = d_ptr, key.ind = d_ind;
+  OnceEntry* entry = nullptr;
+  int rc = once_plan(stream, key, &entry);
   if (rc)
     return rc;
+  spblas_b200_plan* p = entry->plan;
   auto execute = [&]() {
     return beta ? spblas_b200_spmv_axpby(p, val_type, alpha, d_values, d_x, beta, d_d, d_y)
                 : spblas_b200_spmv(p, val_type, alpha, d_values, d_x, d_y);
   };
-  OnceKey key;
-  key.format = format, key.off_type = off_type, key.idx_type = idx_type;
-  key.m = m, key.n = n, key.nnz = nnz, key.ptr = d_ptr, key.ind = d_ind;
-  // ---- the structure of the previous call, if the offsets array still holds what it held ----
+  // ---- a structure seen before, if the offsets array still holds what it held ---------------
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(p->stream, &cap);
-  if (g_once.cached && key == g_once.key && format == SPBLAS_B200_CSR && m > 0 &&
-      p->fp_status_h && cap == cudaStreamCaptureStatusNone) {
+  if (entry->cached && format == SPBLAS_B200_CSR && m > 0 && p->fp_status_h &&
+      cap == cudaStreamCaptureStatusNone) {
     const unsigned int seq = ++p->fp_seq == 0 ? ++p->fp_seq : p->fp_seq;
     p->inspected = true;
     rc = verify_structure(p, seq);
@@ -712,10 +751,10 @@ static int spmv_once_impl(void* stream, int format, int64_t m, int64_t n, int64_
         return SPBLAS_B200_SUCCESS;
     }
     p->inspected = false;
-    g_once.cached = false; // changed in place (or the check could not run): start over
+    entry->cached = false; // changed in place (or the check could not run): start over
   }
   // ---- a structure not seen before: light inspect (validates, leaves the fingerprint) --------
-  g_once.cached = false;
+  entry->cached = false;
   if (!p->fp_status_h) {
     void* h = nullptr;
     if (cudaHostAlloc(&h, sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
@@ -733,8 +772,8 @@ static int spmv_once_impl(void* stream, int format, int64_t m, int64_t n, int64_
   if (rc)
     g_once_error = p->err;
   else if (p->fp_status_d) {
-    g_once.cached = true; // the next call may reuse this plan — after the device-side check
-    g_once.key = key;
+    entry->cached = true; // a later call may reuse this plan — after the device-side check
+    entry->key = key;
   }
   // the one-shot plan never trusts the caller's structure pointers between calls
   p->inspected = false;
@@ -763,12 +802,7 @@ int spblas_b200_spmv_axpby_once(void* stream, int format, int64_t m, int64_t n,
                         alpha, d_values, d_x, beta, d_d, d_y);
 }
 
-void spblas_b200_once_release(void) {
-  if (g_once.plan)
-    spblas_b200_plan_destroy(g_once.plan);
-  g_once.plan = nullptr;
-  g_once.cached = false;
-}
+void spblas_b200_once_release(void) { g_once.release_all_entries(); }
 
 static int spmm_once_impl(void* stream, int format, int64_t m, int64_t n, int64_t nnz,
                           const void* d_ptr, const void* d_ind, int off_type, int idx_type,
@@ -776,11 +810,15 @@ static int spmm_once_impl(void* stream, int format, int64_t m, int64_t n, int64_
                           const void* d_B, int64_t ldb, const void* beta, const void* d_D,
                           int64_t ldd, void* d_C, int64_t ldc, int64_t k) {
   g_once_error.clear();
-  spblas_b200_plan* p = nullptr;
-  int rc = once_plan(stream, &p);
+  OnceKey key; // SpMM keeps no structure between calls: one entry of its own (format -2),
+  key.format = -2; // whose buffers every SpMM one-shot call reuses
+  OnceEntry* entry = nullptr;
+  int rc = once_plan(stream, key, &entry);
   if (rc)
     return rc;
-  g_once.cached = false; // the plan is about to hold another structure
+  spblas_b200_plan* p = entry->plan;
+  entry->cached = true;
+  entry->key = key;
   // SpMM wants to know about very long rows, so this is a full inspect.
   rc = spblas_b200_inspect(p, format, m, n, nnz, d_ptr, d_ind, off_type, idx_type,
                            k, SPBLAS_B200_INSPECT_DEFAULT);

@@ -472,6 +472,22 @@ int inspect_rows(spblas_b200_plan* p, const O* rowptr, int64_t rows, int flags) 
   return SPBLAS_B200_SUCCESS;
 }
 
+// minor indices of a CSC operand must lie inside the matrix: the radix sort below looks at
+// the low bits only, an index outside would silently corrupt the image
+template <typename I>
+__global__ void __launch_bounds__(256)
+index_range_kernel(const I* __restrict__ ind, int64_t nnz, int64_t bound,
+                   unsigned long long* __restrict__ flag) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  bool bad = false;
+  for (int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < nnz; k += stride) {
+    const int64_t v = int64_t(ld_stream(ind + k));
+    bad = bad || v < 0 || v >= bound;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0)
+    atomicOr(flag, 1ull);
+}
+
 template <typename I, typename O>
 int build_row_major_image(spblas_b200_plan* p) {
   // CSC storage: ptr = colptr[n+1], ind = rowind[nnz].  Stable radix sort of the
@@ -525,6 +541,21 @@ int build_row_major_image(spblas_b200_plan* p) {
     if (nnz > int64_t(0x7fffffff))
       return fail(p, SPBLAS_B200_NOT_SUPPORTED,
                   "CSC inspect supports at most 2^31-1 stored entries");
+    {
+      if ((rc = reserve(p, p->seg_counter, sizeof(unsigned long long))))
+        return rc;
+      auto* flag = static_cast<unsigned long long*>(p->seg_counter.p);
+      B200_CUDA_TRY(p, cudaMemsetAsync(flag, 0, sizeof(unsigned long long), s));
+      const int grid = int(std::min<int64_t>((nnz + 255) / 256, int64_t(p->num_sms) * 16));
+      index_range_kernel<I><<<grid, 256, 0, s>>>(rowind + base, nnz, rows, flag);
+      if (int e = launch_ok(p, "index_range_kernel"))
+        return e;
+      unsigned long long outside = 0;
+      B200_CUDA_TRY(p, cudaMemcpyAsync(&outside, flag, sizeof(outside), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+      if (outside)
+        return fail(p, SPBLAS_B200_INVALID_STRUCTURE, "index outside the matrix");
+    }
     int end_bit = 1;
     while (end_bit < int(sizeof(I) * 8) && (int64_t(1) << end_bit) < rows)
       ++end_bit;

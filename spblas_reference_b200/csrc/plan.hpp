@@ -134,13 +134,13 @@ struct spblas_b200_plan {
   cudaGraphExec_t trsv_graph[2] = {nullptr, nullptr};
   cudaStream_t trsv_capture_stream = nullptr;
   b200::DeviceBuffer trsv_params;        // operands of the current solve, read by the graph's kernels
+  cudaEvent_t trsv_done_event = nullptr; // end of the last graph replay (orders the next rewrite of trsv_params)
 
   // ---- merge-path partition --------------------------------------------------
   int tile_items = b200::kSpmvTileItems;
   int tile_items_override = 0; // env SPBLAS_B200_TILE_ITEMS (tuning)
   int stages = 0;              // env SPBLAS_B200_STAGES (0 = default)
   int ctas_per_sm = 0;         // env SPBLAS_B200_CTAS_PER_SM (0 = default)
-  int consumer_warps = 0;      // env SPBLAS_B200_CONSUMER_WARPS (8 or 16; 0 = default)
   int64_t num_tiles = 0;
   int64_t uniform_tiles = 0;      // tiles whose complete rows share one length <= 8
   b200::DeviceBuffer tile_starts; // int64 (row, nnz) pairs, num_tiles + 1 entries

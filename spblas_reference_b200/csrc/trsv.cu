@@ -65,10 +65,22 @@ trsv_relax_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind, in
 template <typename I, typename O>
 __global__ void __launch_bounds__(256)
 trsv_check_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind, int64_t m,
-                  int* __restrict__ row_ids, unsigned long long* __restrict__ stats) {
+                  int64_t nnz, int* __restrict__ row_ids,
+                  unsigned long long* __restrict__ stats) {
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  // the offsets first: every later kernel walks colind through them, and the buffers of the
+  // column structure are sized by the caller's nnz
+  const int64_t first = int64_t(rowptr[0]), last = int64_t(rowptr[m]);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (first < 0 || last - first != nnz))
+    atomicAdd(&stats[3], 1ull);
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < m; i += stride) {
     bool diag = false, bad = false;
+    const int64_t lo = int64_t(rowptr[i]), hi = int64_t(rowptr[i + 1]);
+    if (hi < lo || lo < first || hi > first + nnz) {
+      atomicAdd(&stats[3], 1ull); // not monotone / outside the arrays: do not follow it
+      row_ids[i] = int(i);
+      continue;
+    }
     for (O p = rowptr[i]; p < rowptr[i + 1]; ++p) {
       const int64_t k = int64_t(colind[p]);
       diag = diag || k == i;
@@ -275,12 +287,15 @@ int trsv_inspect_typed(spblas_b200_plan* p, int64_t m, const void* d_rowptr,
   B200_CUDA_TRY(p, cudaMemsetAsync(stats, 0, 16 * sizeof(unsigned long long), s));
   const int grid = int(std::min<int64_t>((m + 255) / 256, int64_t(p->num_sms) * 16));
   // structure first: the sweeps below index level[] with the column indices
-  trsv_check_kernel<I, O><<<grid, 256, 0, s>>>(rowptr, colind, m, row_ids, stats);
+  trsv_check_kernel<I, O><<<grid, 256, 0, s>>>(rowptr, colind, m, p->trsv_nnz, row_ids, stats);
   if (int rc = check(p, "trsv_check_kernel"))
     return rc;
-  unsigned long long h_stats[3] = {0, 0, 0};
+  unsigned long long h_stats[4] = {0, 0, 0, 0};
   B200_CUDA_TRY(p, cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, s));
   B200_CUDA_TRY(p, cudaStreamSynchronize(s));
+  if (h_stats[3] > 0)
+    return fail(p, SPBLAS_B200_INVALID_STRUCTURE,
+                "offsets array is not monotone or does not span nnz entries");
   if (h_stats[2] > 0)
     return fail(p, SPBLAS_B200_INVALID_STRUCTURE, "column index outside the matrix");
   if (!unit && h_stats[1] > 0)
@@ -392,6 +407,10 @@ int trsv_solve_typed(spblas_b200_plan* p, const void* alpha_a, const void* alpha
     h.alpha_b = double(ab);
     h.has_aa = alpha_a != nullptr;
     h.has_ab = alpha_b != nullptr;
+    // the previous solve's kernels read the parameter block: if that solve ran on another
+    // stream (set_stream between solves), this copy must wait for it
+    if (p->trsv_done_event)
+      B200_CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->trsv_done_event, 0));
     B200_CUDA_TRY(p, cudaMemcpyAsync(p->trsv_params.p, &h, sizeof(h), cudaMemcpyHostToDevice,
                                      p->stream));
     if (!p->trsv_graph[slot]) {
@@ -422,6 +441,9 @@ int trsv_solve_typed(spblas_b200_plan* p, const void* alpha_a, const void* alpha
       }
     }
     B200_CUDA_TRY(p, cudaGraphLaunch(p->trsv_graph[slot], p->stream));
+    if (!p->trsv_done_event)
+      B200_CUDA_TRY(p, cudaEventCreateWithFlags(&p->trsv_done_event, cudaEventDisableTiming));
+    B200_CUDA_TRY(p, cudaEventRecord(p->trsv_done_event, p->stream));
     p->last_launches = p->trsv_levels;
     p->total_launches += p->trsv_levels;
     return SPBLAS_B200_SUCCESS;

@@ -168,7 +168,7 @@ def test_no_info_overload_notices_a_structure_changed_in_place(cuda, oracle):
 def test_no_info_overload_alternating_matrices_and_streams(cuda, oracle):
     rng = np.random.default_rng(22)
     mats = []
-    for i, kind in enumerate(["short", "mixed"]):
+    for i, kind in enumerate(["short", "hubrow"]):
         m, n = 2000 + 100 * i, 1500
         v, rp, ci, x = _skewed_csr(rng, m, n, _lens(rng, m, kind), np.float64)
         mats.append((csr_on_device(v, rp, ci, (m, n)), dev(x), v, rp, ci, x, m, n))

@@ -167,3 +167,60 @@ def test_trsv_level_analysis_variants(cuda, oracle, monkeypatch, inspect):
         assert np.array_equal(_solve(a, upper, 0, b, m, info=info),
                               oracle.trsv(m, rp, ci, v, b, upper=upper, unit=False), equal_nan=True)
         info.close()
+
+
+def test_c_abi_guards_found_by_review(cuda, oracle):
+    """Round-1 review: (1) spblas_b200_inspect on a plan that holds a triangular
+    structure must invalidate it — the two share index types and owned buffers, and a later
+    spblas_b200_trsv would read the triangle with the new widths; (2) trsv_inspect must not
+    trust the caller's nnz or an offsets array that is not monotone."""
+    import ctypes as C
+    from spblas_reference_b200 import _cabi
+    L = _cabi.lib()
+    rng = np.random.default_rng(8)
+    m = 500
+    v, rp, ci = _tri_matrix(rng, m, "short", np.float64, np.int64, np.int64)
+    a64 = csr_on_device(v, rp, ci, (m, m))
+    b = dev(rng.standard_normal(m))
+    x = torch.empty(m, dtype=torch.float64, device="cuda")
+    info = sb.triangular_solve_inspect(a64, sb.lower_triangle, sb.implicit_unit_diagonal, b, x)
+    # the same plan now inspects an int32 matrix for a product ...
+    a32 = csr_on_device(v.astype(np.float64), rp.astype(np.int32), ci.astype(np.int32), (m, m))
+    st = L.spblas_b200_inspect(info._plan, _cabi.CSR, m, m, a32.nnz, a32.rowptr.data_ptr(),
+                               a32.colind.data_ptr(), _cabi.I32, _cabi.I32, 1, 0)
+    assert st == _cabi.SUCCESS
+    # ... and the triangular solve must refuse instead of walking int64 arrays as int32
+    st = L.spblas_b200_trsv(info._plan, _cabi.F64, None, None, a64.values.data_ptr(),
+                            b.data_ptr(), x.data_ptr())
+    assert st == _cabi.NOT_INSPECTED
+    info.close()
+
+    plan = C.c_void_p()
+    assert L.spblas_b200_plan_create(C.byref(plan), None) == 0
+    try:
+        a = csr_on_device(v, rp.astype(np.int32), ci.astype(np.int32), (m, m))
+        st = L.spblas_b200_trsv_inspect(plan, m, a.nnz + 7, a.rowptr.data_ptr(),
+                                        a.colind.data_ptr(), _cabi.I32, _cabi.I32, 0, 1)
+        assert st == _cabi.INVALID_STRUCTURE, L.spblas_b200_last_error(plan)
+        bad = rp.astype(np.int32).copy()
+        bad[10], bad[11] = bad[11] + 3, bad[10]
+        badp = dev(bad)
+        st = L.spblas_b200_trsv_inspect(plan, m, a.nnz, badp.data_ptr(), a.colind.data_ptr(),
+                                        _cabi.I32, _cabi.I32, 0, 1)
+        assert st == _cabi.INVALID_STRUCTURE
+        st = L.spblas_b200_trsv_inspect(plan, m, a.nnz, a.rowptr.data_ptr(), a.colind.data_ptr(),
+                                        _cabi.I32, _cabi.I32, 0, 1)
+        assert st == _cabi.SUCCESS
+    finally:
+        L.spblas_b200_plan_destroy(plan)
+
+
+def test_csc_index_outside_the_matrix_is_refused(cuda):
+    """A row index >= m in a CSC operand: the image builder's sort looks at the low bits only,
+    so the inspect phase must check the range itself."""
+    from helpers import csc_on_device
+    colptr = np.array([0, 2, 3, 5], np.int32)
+    rowind = np.array([0, 9, 1, 2, 3], np.int32)          # 9 >= m = 4
+    a = csc_on_device(np.ones(5, np.float32), colptr, rowind, (4, 3))
+    with pytest.raises(RuntimeError, match="outside the matrix"):
+        sb.multiply_inspect(a, torch.ones(3, device="cuda"), torch.empty(4, device="cuda"))
