@@ -102,11 +102,21 @@ def check_spmv(rp, ci, v, x, alpha, y_dev, rows, n, what, reps=1):
     return cpu, parity
 
 
-def check_spmm(rp, ci, v, B, alpha, C_dev, rows, n, what):
+def check_spmm(rp, ci, v, B, alpha, C_dev, rows, n, what, compact=False):
+    """compact: B is too large for the host (C5: 34 GB) — the reference multiplies the sampled
+    rows against the rows of B they reference, renumbered in ascending order: the same products
+    in the same order."""
     O, impl, kind = _oracle()
     r0, r1 = rows
     rph, cih, vh = _host_rows(rp, ci, v, r0, r1)
-    Bh = B.cpu().numpy()
+    if compact:
+        cols = np.unique(cih)
+        cih = np.searchsorted(cols, cih).astype(cih.dtype)
+        Bh = B[torch.from_numpy(cols.astype(np.int64)).to(B.device)].cpu().numpy()
+        n = len(cols)
+        what += f" (against the {n} rows of B it references)"
+    else:
+        Bh = B.cpu().numpy()
     k = Bh.shape[1]
     t0 = time.perf_counter()
     Cref, used = _ref_call(O, O.spmm, impl, "csr", (r1 - r0, n), rph, cih, vh, Bh, alpha_a=alpha)
@@ -195,9 +205,11 @@ SPMV_KERNEL = {0: "spmv_merge_tile_kernel", 1: "spmv_pipe_kernel", 2: "spmv_warp
                3: "spmv_hub_stream_kernel", 4: "spmv_hubg_stream_kernel"}
 
 
-def _free(*names):
-    torch.cuda.synchronize()
-    torch.cuda.empty_cache()
+def _progress(ctx, msg):
+    """stderr breadcrumbs of the long blocks (SPBLAS_B200_BENCH_VERBOSE=1)."""
+    if os.environ.get("SPBLAS_B200_BENCH_VERBOSE") == "1" and ctx.get("rank", 0) == 0:
+        import sys
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
 # --------------------------------------------------------------------------------------------
@@ -359,9 +371,11 @@ def config_c5(ctx, scale=27, with_spmm=True):
     barrier, max_over_ranks, sum_over_ranks = ctx["barrier"], ctx["max"], ctx["sum"]
     n = 1 << scale
     t0 = time.perf_counter()
+    _progress(ctx, f"c5: generating scale {scale}")
     v, rp, ci, shape, blocks, max_deg = _c5_block(ctx, scale)
     torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
+    _progress(ctx, f"c5: generated {int(ci.numel())} entries in {gen_s:.1f} s")
     m_loc, nnz_loc = shape[0], int(ci.numel())
     r0, r1 = blocks[rank]
     a_plain = sb.csr_view(v, rp, ci, shape, nnz_loc)
@@ -377,10 +391,12 @@ def config_c5(ctx, scale=27, with_spmm=True):
     info = sb.multiply_inspect(a, x0, y_tmp)
     torch.cuda.synchronize()
     inspect_ms = (time.perf_counter() - t0) * 1e3
+    _progress(ctx, f"c5: inspected in {inspect_ms:.1f} ms")
     t0 = time.perf_counter()
     sb.multiply_execute(info, a_scaled, x0, y_tmp)      # first product: builds the lazy tables
     torch.cuda.synchronize()
     first_ms = (time.perf_counter() - t0) * 1e3
+    _progress(ctx, f"c5: first product {first_ms:.1f} ms, variant {info.spmv_variant}, hubs {info.hub_count}")
     # the plain operand (no matrix_opt) beside it: kernel only
     info_plain = sb.multiply_inspect(a_plain, x0, y_tmp)
     plain_ms = max_over_ranks(time_loop(
@@ -392,6 +408,7 @@ def config_c5(ctx, scale=27, with_spmm=True):
                      torch.float64, dev, info=info,
                      fused=None if os.environ.get("SPBLAS_B200_FUSED", "1") != "0" else False,
                      multicast={"1": True, "0": False}.get(os.environ.get("SPBLAS_B200_MULTICAST")))
+    _progress(ctx, f"c5: plain operand {plain_ms:.3f} ms; exchange {op.exchange_impl}")
     op.set_x(x0)
     del x0
     Kc = max(3, min(K, 10))
@@ -417,6 +434,7 @@ def config_c5(ctx, scale=27, with_spmm=True):
     barrier()
     kern_ms = max_over_ranks(k0.elapsed_time(k1) / Kc)
 
+    _progress(ctx, f"c5: step {step_ms:.3f} ms, kernels {kern_ms:.3f} ms")
     # ---- parity after >= 3 fused iterations: (1) this rank's replica of x is bit for bit what an
     # out-of-band allgather of the blocks gives, (2) its rows of the next product are within the
     # bound of the reference's CPU multiply fed with the same x (per iteration, not compounded)
@@ -455,6 +473,7 @@ def config_c5(ctx, scale=27, with_spmm=True):
     if op.fused:                                          # plain products again
         info.set_scatter(())
         info.set_barrier((), ())
+    _progress(ctx, f"c5: parity {parity['max_err_over_tol']:.3f} pass {parity['pass']}")
     # ---- end to end: every rank uploads x and downloads its block, every step
     e2e, _ = e2e_spmv(sb, info, a_scaled, x_in, m_loc, flops, steps=3)
     e2e["ms_per_step"] = max_over_ranks(e2e["ms_per_step"])
@@ -496,6 +515,7 @@ def config_c5(ctx, scale=27, with_spmm=True):
         return out
 
     # ---- the SpMM half: C = A B, k = 32, B replicated, no exchange -------------------------
+    _progress(ctx, f"c5: e2e {e2e['ms_per_step']:.1f} ms; SpMM half next")
     k = 32
     torch.cuda.empty_cache()
     B = G.dense_uniform_rows(n, k, 6, torch.float64, dev)
@@ -514,9 +534,10 @@ def config_c5(ctx, scale=27, with_spmm=True):
     e1.record()
     barrier()
     mm_ms = max_over_ranks(e0.elapsed_time(e1) / Km)
+    _progress(ctx, f"c5mm: {mm_ms:.2f} ms, variant {info_mm.spmm_variant}")
     rows_mm = int(min(m_loc, 20_000))
     cpu_mm, par_mm = check_spmm(rp, ci, v, B, None, C[:rows_mm], (0, rows_mm), n,
-                                f"C5 SpMM scale {scale} rank {rank} row sample")
+                                f"C5 SpMM scale {scale} rank {rank} row sample", compact=True)
     par_mm["max_err_over_tol"] = max_over_ranks(par_mm["max_err_over_tol"])
     par_mm["rows_checked"] = int(sum_over_ranks(par_mm["rows_checked"]))
     par_mm["pass"] = bool(max_over_ranks(0.0 if par_mm["pass"] else 1.0) == 0.0)

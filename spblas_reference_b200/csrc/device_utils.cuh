@@ -156,6 +156,34 @@ __device__ __forceinline__ uint4 ld_ro_16_el(const void* p) {
   return r;
 }
 
+// L1 eviction priorities for gathers (experiments of round 2: the compact hub table kept in
+// L1, the cold gathers out of it)
+template <typename T>
+__device__ __forceinline__ T ld_ro_l1_evict_last(const T* p) {
+  if constexpr (sizeof(T) == 4) {
+    uint32_t r;
+    asm("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return *reinterpret_cast<T*>(&r);
+  } else {
+    unsigned long long r;
+    asm("ld.global.nc.L1::evict_last.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return *reinterpret_cast<T*>(&r);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T ld_ro_l1_evict_first(const T* p) {
+  if constexpr (sizeof(T) == 4) {
+    uint32_t r;
+    asm("ld.global.nc.L1::evict_first.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return *reinterpret_cast<T*>(&r);
+  } else {
+    unsigned long long r;
+    asm("ld.global.nc.L1::evict_first.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return *reinterpret_cast<T*>(&r);
+  }
+}
+
 // EF = true: the streamed-once flavour with the evict_first hint
 template <bool EF, typename T>
 __device__ __forceinline__ Quad<T> ld_stream_quad_p(const T* p) {

@@ -339,8 +339,9 @@ int launch_fingerprint(spblas_b200_plan* p, const O* rowptr, int64_t rows, int c
   if (!compare)
     B200_CUDA_TRY(p, cudaMemsetAsync(static_cast<char*>(p->fp_state.p) + offsetof(HashState, bad),
                                      0, sizeof(unsigned int), p->stream));
+  // one CTA per SM at most: the launch ends with one atomic per CTA on a single word
   const int64_t want = (rows + 1 + 255) / 256;
-  const int grid = int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(p->num_sms) * 8)));
+  const int grid = int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(p->num_sms))));
   offsets_fingerprint_kernel<O><<<grid, 256, 0, p->stream>>>(
       rowptr, rows, p->nnz, static_cast<HashState*>(p->fp_state.p), compare, seq,
       p->fp_status_d);

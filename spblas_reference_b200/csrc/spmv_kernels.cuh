@@ -908,9 +908,22 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
             if constexpr (HUB == 1) {
               xv[j] = c.v[j] < I(0) ? ld_hub<T>(hub, int(~c.v[j])) : ws_gather<true>(x + c.v[j]);
             } else if constexpr (HUB == 2) {
-              // one load either way: a negative index reads the compact table
+              // a negative index reads the compact table.  L1 policy (build-time switch
+              // B200_HUBG_L1, measured on the scale-27 shard, profiles/
+              // r02_hubg_l1_priorities.jsonl): 0 one plain load either way 1.92 ms; 1 table
+              // lines evict_last 1.88 ms; 2 (default) table evict_last AND the cold gathers of
+              // x not allocated in L1 — they come from DRAM and would only push the table's
+              // lines out — 1.69 ms; 3 cold gathers evict_first 1.73 ms.
               const bool h = c.v[j] < I(0);
+#if defined(B200_HUBG_L1) && B200_HUBG_L1 == 0
               xv[j] = ld_ro((h ? xh : x) + (h ? ~c.v[j] : c.v[j]));
+#elif defined(B200_HUBG_L1) && B200_HUBG_L1 == 1
+              xv[j] = h ? ld_ro_l1_evict_last(xh + ~c.v[j]) : ld_ro(x + c.v[j]);
+#elif defined(B200_HUBG_L1) && B200_HUBG_L1 == 3
+              xv[j] = h ? ld_ro(xh + ~c.v[j]) : ld_ro_l1_evict_first(x + c.v[j]);
+#else
+              xv[j] = h ? ld_ro_l1_evict_last(xh + ~c.v[j]) : ld_stream(x + c.v[j]);
+#endif
             } else {
               xv[j] = ws_gather<false>(x + c.v[j]);
             }

@@ -390,3 +390,41 @@ def test_matrix_opt_caches_values_of_a_transposed_operand(cuda, oracle, monkeypa
                              oracle.abs_rowsum(t_rp, t_ci, v2[perm], x), "matrix_opt re-inspected")
     for i in (info_plain, info, i1, i2):
         i.close()
+
+
+@pytest.mark.parametrize("stages", ["2", "3", "4", "6", "8"])
+def test_pipe_kernel_ragged_last_tile_every_stage_count(cuda, oracle, monkeypatch, stages):
+    """The pipelined kernel's last tile mixes plain stores (zero fill past the arrays' end),
+    element-wise cp.async (the last partial quad, the row ends) and TMA bulk copies on ONE
+    stage of the ring; racecheck cannot model their completion mechanism (cp.async.mbarrier.
+    arrive.noinc), so this settles it by execution: nnz % 4 = 0..3, rows uniform (exact path)
+    and mixed (flat path), every ring depth, 25 executes each into a poisoned y — integer
+    scalars, so a single stale or torn operand shows as an exact mismatch."""
+    monkeypatch.setenv("SPBLAS_B200_SPMV_VARIANT", "1")
+    monkeypatch.setenv("SPBLAS_B200_STAGES", stages)
+    rng = np.random.default_rng(int(stages))
+    n = 1531
+    for uniform in (True, False):
+        for tail in range(4):
+            # a few tiles' worth of rows (2048 merge items per tile), then trim to nnz % 4 == tail
+            m = 3 * 2048 // 6 + 17
+            lens = np.full(m, 5, dtype=np.int64) if uniform else rng.integers(0, 11, size=m)
+            while int(lens.sum()) % 4 != tail:
+                lens[-1 - int(rng.integers(0, 3))] += 1
+            rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+            nnz = int(rp[-1])
+            ci = rng.integers(0, n, size=nnz).astype(np.int32)
+            v = rng.integers(-9, 10, size=nnz).astype(np.int32)
+            x = rng.integers(-9, 10, size=n).astype(np.int32)
+            want = oracle.spmv("csr", (m, n), rp, ci, v, x)
+            # values / colind end exactly at the allocation's end: a read past nnz would fault
+            a = csr_on_device(v, rp, ci, (m, n))
+            xd = dev(x)
+            y = torch.empty(m, dtype=torch.int32, device="cuda")
+            info = sb.multiply_inspect(a, xd, y)
+            for rep in range(25):
+                y.fill_(77)
+                sb.multiply_execute(info, a, xd, y)
+                assert info.spmv_variant == 1
+                assert np.array_equal(y.cpu().numpy(), want), (uniform, tail, stages, rep)
+            info.close()
