@@ -434,6 +434,8 @@ def config_c5(ctx, scale=27, with_spmm=True):
     barrier()
     kern_ms = max_over_ranks(k0.elapsed_time(k1) / Kc)
 
+    variant_used = info.spmv_variant          # (the host-buffer e2e leg below runs the plain walk)
+    hub_columns, hub_refs = info.hub_count, info.hub_refs
     _progress(ctx, f"c5: step {step_ms:.3f} ms, kernels {kern_ms:.3f} ms")
     # ---- parity after >= 3 fused iterations: (1) this rank's replica of x is bit for bit what an
     # out-of-band allgather of the blocks gives, (2) its rows of the next product are within the
@@ -490,8 +492,8 @@ def config_c5(ctx, scale=27, with_spmm=True):
           "kernel_only_ms": kern_ms, "kernel_only_gflops": flops / kern_ms / 1e6,
           "generate_s": gen_s, "inspect_ms": inspect_ms, "first_execute_ms": first_ms,
           "max_row_len": info.max_row_len,
-          "spmv_variant": info.spmv_variant, "gpu_launches": launches,
-          "hub_columns": info.hub_count, "hub_reference_share": info.hub_refs / max(nnz_loc, 1),
+          "spmv_variant": variant_used, "gpu_launches": launches,
+          "hub_columns": hub_columns, "hub_reference_share": hub_refs / max(nnz_loc, 1),
           "plain_operand": {"kernel_only_ms": plain_ms, "spmv_variant": plain_variant,
                             "what": "the same product without matrix_opt (warp-stream kernel)"},
           "exchange": {"mode": op.plan.mode,
@@ -502,8 +504,8 @@ def config_c5(ctx, scale=27, with_spmm=True):
           "l2_policy": "inputs larger than L2",
           "roofline": roofline(nbytes, kern_ms, ctx["peak"], ctx["peak_src"],
                                ctx["traffic"](f"c5_n{world}"),
-                               SPMV_KERNEL.get(info.spmv_variant, "?") + "<double,int,long>"
-                               + (" (+ hub_fill_kernel)" if info.spmv_variant == 4 else "")),
+                               SPMV_KERNEL.get(variant_used, "?") + "<double,int,long>"
+                               + (" (+ hub_fill_kernel)" if variant_used == 4 else "")),
           "cpu_baseline": cpu if rank == 0 else None, "e2e": e2e, "parity": parity}
     c5["roofline"]["note"] = ("per GPU: this rank-0-timed launch streams its block of A and gathers "
                               "from the full replicated x (1.07 GB at scale 27: beyond L2, so a gather "

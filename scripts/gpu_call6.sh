@@ -2,7 +2,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 echo "== default bench, as the driver runs it (N=1, every config, C5 at scale 27)"
-SECONDS=0; SPBLAS_B200_BENCH_VERBOSE=1 timeout 1500 python -X faulthandler bench.py --configs c5 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
+SECONDS=0; SPBLAS_B200_BENCH_VERBOSE=1 timeout 1500 python -X faulthandler bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
 echo "wall seconds: $SECONDS"
 tail -c 1500 gpurun_out/r2_bench_n1.err
 python - <<'PY'
@@ -19,12 +19,3 @@ except Exception as e:
     print("parse failed", e)
 PY
 nvidia-smi --query-gpu=memory.used --format=csv
-echo "== L1 eviction priorities in the global-hub walk"
-for lib in base l1p1 l1p2 l1p3; do
-  L=""; [ $lib != base ] && L=$PWD/spblas_reference_b200/libspblas_b200_$lib.so
-  for cols in 262144 1000000; do
-    SPBLAS_B200_LIB=$L EXP_VARIANT=4 EXP_HUB_COLS=$cols timeout 300 python scripts/exp_r2.py spmv c4 30 2>&1 | cut -c1-260
-  done
-  SPBLAS_B200_LIB=$L EXP_MATRIX_OPT=1 timeout 400 python scripts/exp_r2.py spmv c5shard 20 2>&1 | cut -c1-260
-done > gpurun_out/r2_hubg_l1_priorities.jsonl
-cat gpurun_out/r2_hubg_l1_priorities.jsonl

@@ -1390,7 +1390,8 @@ spmv_carry_fixup_kernel(const int64_t* __restrict__ carry_row,
   __syncthreads();
   if (!s_last || int(threadIdx.x) >= bar.n)
     return;
-  __threadfence_system();
+  // (st.release.sys orders everything this thread observed — the block counter's chain — before
+  // the flag: no separate system fence)
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(bar.remote[threadIdx.x]),
                "l"(bar.epoch)
                : "memory");
