@@ -459,6 +459,15 @@ def config_c5(ctx, scale=27, with_spmm=True):
     # the sample: the block's first rows (rank 0's are the densest of the matrix)
     cpu, parity = check_spmv(rp, ci, v, x_in, alpha, y_blk[:rows_n], (0, rows_n), n,
                              f"C5 scale {scale} rank {rank} row sample")
+    # ... and its LAST rows: at N = 1 their offsets lie beyond 2^31 - 1 (the reason this config
+    # has 64-bit offsets)
+    if m_loc > rows_n:
+        t0_, t1_ = max(rows_n, m_loc - rows_n), m_loc
+        _, par_tail = check_spmv(rp, ci, v, x_in, alpha, y_blk[t0_:t1_], (t0_, t1_), n, "tail rows")
+        parity["max_err_over_tol"] = max(parity["max_err_over_tol"], par_tail["max_err_over_tol"])
+        parity["rows_checked"] += par_tail["rows_checked"]
+        parity["pass"] = parity["pass"] and par_tail["pass"]
+        parity["largest_offset_checked"] = int(rp[-1])
     parity["max_err_over_tol"] = max_over_ranks(parity["max_err_over_tol"])
     parity["rows_checked"] = int(sum_over_ranks(parity["rows_checked"]))
     parity["pass"] = bool(max_over_ranks(0.0 if parity["pass"] else 1.0) == 0.0)

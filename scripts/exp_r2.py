@@ -78,10 +78,26 @@ def spmv_workload(wl):
     raise SystemExit(f"unknown workload {wl}")
 
 
+def set_persisting_l2(mb):
+    """cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize): the set-aside L2::evict_last lines live in"""
+    import ctypes
+    import torch
+    torch.cuda.init()
+    rt = ctypes.CDLL("libcudart.so.12")
+    size = ctypes.c_size_t(0)
+    rc = rt.cudaDeviceSetLimit(6, ctypes.c_size_t(mb << 20))
+    rt.cudaDeviceGetLimit(ctypes.byref(size), 6)
+    prop_max = torch.cuda.get_device_properties(0)
+    print(json.dumps({"persisting_l2_request_mb": mb, "rc": rc, "granted_mb": size.value >> 20,
+                      "L2_cache_size_mb": prop_max.L2_cache_size >> 20}), flush=True)
+
+
 def run_spmv(wl, reps):
     import torch
     import spblas_reference_b200 as sb
     from spblas_reference_b200 import _cabi
+    if os.environ.get("EXP_PERSIST_L2_MB"):
+        set_persisting_l2(int(os.environ["EXP_PERSIST_L2_MB"]))
     sets = spmv_workload(wl)
     ops = []
     opt = os.environ.get("EXP_MATRIX_OPT", "0") == "1"      # wrap in matrix_opt (hub tables)

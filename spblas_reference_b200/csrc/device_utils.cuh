@@ -171,6 +171,26 @@ __device__ __forceinline__ T ld_ro_l1_evict_last(const T* p) {
   }
 }
 
+// ... kept in L1 AND in L2 (the compact hub table: the one operand worth pinning)
+template <typename T>
+__device__ __forceinline__ T ld_ro_keep(const T* p) {
+  if constexpr (sizeof(T) == 4) {
+    uint32_t r;
+    asm("{\n.reg .b64 pol;\n" B200_POLICY_EL
+        "ld.global.nc.L1::evict_last.L2::cache_hint.u32 %0, [%1], pol;\n}"
+        : "=r"(r)
+        : "l"(p));
+    return *reinterpret_cast<T*>(&r);
+  } else {
+    unsigned long long r;
+    asm("{\n.reg .b64 pol;\n" B200_POLICY_EL
+        "ld.global.nc.L1::evict_last.L2::cache_hint.u64 %0, [%1], pol;\n}"
+        : "=l"(r)
+        : "l"(p));
+    return *reinterpret_cast<T*>(&r);
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ T ld_ro_l1_evict_first(const T* p) {
   if constexpr (sizeof(T) == 4) {

@@ -820,6 +820,12 @@ __device__ __forceinline__ T ld_hub(uint32_t hub, int slot) {
 #define B200_WS_X_EL 0
 #endif
 constexpr bool kWsStreamEF = B200_WS_A_EF != 0;
+// the global-hub walk (x larger than L2): the compact table is the one operand worth keeping
+// in L2 — its loads carry evict_last, the streams of A and the cold gathers evict_first
+#ifndef B200_HUBG_L2
+#define B200_HUBG_L2 0
+#endif
+constexpr bool kHubgL2 = B200_HUBG_L2 != 0;
 
 template <bool CG, typename T>
 __device__ __forceinline__ T ws_gather(const T* p) {
@@ -883,11 +889,11 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
           Quad<I> c;
           Quad<T> v;
           if (kk + 4 <= arr_end) {
-            c = ld_stream_quad_p<kWsStreamEF>(ci + kk);
+            c = ld_stream_quad_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(ci + kk);
             if (!has_perm) {
-              v = ld_stream_quad_p<kWsStreamEF>(va + kk);
+              v = ld_stream_quad_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(va + kk);
             } else {
-              const Quad<O> pi = ld_stream_quad_p<kWsStreamEF>(perm + base + kk);
+              const Quad<O> pi = ld_stream_quad_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(perm + base + kk);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 v.v[j] = ld_ro(values + pi.v[j]);
@@ -896,10 +902,10 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const bool in = kk + j < arr_end;
-              c.v[j] = in ? ld_stream_p<kWsStreamEF>(ci + kk + j) : I(0);
+              c.v[j] = in ? ld_stream_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(ci + kk + j) : I(0);
               v.v[j] = !in ? T(0)
                            : (has_perm ? ld_ro(values + perm[base + kk + j])
-                                       : ld_stream_p<kWsStreamEF>(va + kk + j));
+                                       : ld_stream_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(va + kk + j));
             }
           }
           T xv[4];
@@ -922,7 +928,10 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
 #elif defined(B200_HUBG_L1) && B200_HUBG_L1 == 3
               xv[j] = h ? ld_ro(xh + ~c.v[j]) : ld_ro_l1_evict_first(x + c.v[j]);
 #else
-              xv[j] = h ? ld_ro_l1_evict_last(xh + ~c.v[j]) : ld_stream(x + c.v[j]);
+              if constexpr (kHubgL2)
+                xv[j] = h ? ld_ro_keep(xh + ~c.v[j]) : ld_stream_ef(x + c.v[j]);
+              else
+                xv[j] = h ? ld_ro_l1_evict_last(xh + ~c.v[j]) : ld_stream(x + c.v[j]);
 #endif
             } else {
               xv[j] = ws_gather<false>(x + c.v[j]);
@@ -936,7 +945,7 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
       // ---- rows that end inside the chunk -------------------------------------------
       int re = 0x7fffffff;
       if (lane < rows_left)
-        re = int(int64_t(ld_stream_p<kWsStreamEF>(rowptr + row + 1 + lane)) - base);
+        re = int(int64_t(ld_stream_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(rowptr + row + 1 + lane)) - base);
       unsigned mask = __ballot_sync(0xffffffffu, re <= kend);
       if (mask == 0u) {
         // the chunk lies inside one row: no shared memory, straight to the shuffle tree
@@ -1005,7 +1014,7 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
             break;
           re = 0x7fffffff;
           if (lane < rows_left)
-            re = int(int64_t(ld_stream_p<kWsStreamEF>(rowptr + row + 1 + lane)) - base);
+            re = int(int64_t(ld_stream_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(rowptr + row + 1 + lane)) - base);
           mask = __ballot_sync(0xffffffffu, re <= kend);
           if (mask == 0u)
             break;
