@@ -133,8 +133,39 @@ def run_spmv(wl, reps):
                       "checksum": float(y.double().sum().item())}), flush=True)
 
 
+def run_spmm_rmat(scale, k, dtype_name):
+    """row kernel vs stream (ring) kernel on a power-law matrix with a narrow B (forced through
+    SPBLAS_B200_SPMM_VARIANT): does the row-length histogram have to steer the choice?"""
+    import torch
+    import spblas_reference_b200 as sb
+    from spblas_reference_b200 import generators as G
+    dev = torch.device("cuda:0")
+    dt = torch.float32 if dtype_name == "fp32" else torch.float64
+    v, rp, ci, shape = G.rmat_csr(scale, 16, seed=24, dtype=dt, device=dev)
+    a = sb.csr_view(v, rp, ci, shape, int(ci.numel()))
+    B = G.dense_uniform((shape[1], k), 4, dt, dev)
+    ref = None
+    for forced in ("0", "1", None):
+        if forced is None:
+            os.environ.pop("SPBLAS_B200_SPMM_VARIANT", None)
+        else:
+            os.environ["SPBLAS_B200_SPMM_VARIANT"] = forced
+        C = torch.empty((shape[0], k), dtype=dt, device=dev)
+        info = sb.multiply_inspect(a, B, C)
+        ms = timed(lambda i: sb.multiply_execute(info, a, B, C), 10)
+        ref = C if ref is None else ref
+        print(json.dumps({"exp": "spmm_rmat", "scale": scale, "k": k, "dtype": dtype_name, "forced": forced,
+                          "variant": info.spmm_variant, "max_row_len": info.max_row_len,
+                          "mean_row_len": round(a.nnz / shape[0], 2), "num_segments": info.num_segments,
+                          "ms": round(ms, 4), "max_abs_diff_vs_first": (C - ref).abs().max().item()}), flush=True)
+        info.close()
+
+
 if __name__ == "__main__":
     mode = sys.argv[1]
+    if mode == "spmm_rmat":
+        run_spmm_rmat(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4])
+        sys.exit(0)
     if mode == "spmv":
         run_spmv(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 30)
     elif mode == "libs":

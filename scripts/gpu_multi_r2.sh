@@ -7,8 +7,12 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 echo "== multi-GPU parity tests (world size $N only: the smaller ones ran on the smaller boxes)"
 SEL="$N"; [ "$N" = "2" ] && SEL="2 or timeout"
+if [ "${SKIP_TESTS:-0}" != "1" ]; then
 timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -k "$SEL" > gpurun_out/r2_multi_tests_n$N.log 2>&1
 tail -4 gpurun_out/r2_multi_tests_n$N.log
+fi
+echo "== where the exchange's cost goes (C2 weak)"
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29544 scripts/exp_exchange.py 2>&1 | tail -1 | tee gpurun_out/r2_exchange_n$N.json
 echo "== bench --gpus $N"
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
   --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 \

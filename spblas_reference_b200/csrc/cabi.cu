@@ -257,6 +257,8 @@ int spblas_b200_plan_create(spblas_b200_plan** out, void* cuda_stream) {
     if (t > 0)
       p->barrier_timeout_ms = (unsigned long long)t;
   }
+  if (const char* v = std::getenv("SPBLAS_B200_LATE_PUSH_ROWS"))
+    p->late_push_max_rows = std::max<long long>(0, std::atoll(v));
   if (const char* v = std::getenv("SPBLAS_B200_HOST_CHUNKS"))
     p->host_chunks_override = std::atoi(v);
   if (const char* v = std::getenv("SPBLAS_B200_SPMM_VARIANT"))

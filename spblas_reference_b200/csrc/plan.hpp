@@ -211,6 +211,9 @@ struct spblas_b200_plan {
   unsigned int* barrier_gave_up_d = nullptr;
   bool barrier_gave_up_seen = false;           // sticky copy for SPBLAS_B200_Q_BARRIER_TIMEOUT
   unsigned long long barrier_timeout_ms = 30000; // env SPBLAS_B200_BARRIER_TIMEOUT_MS
+  // an exchange of at most this many rows is pushed by the fix-up kernel's last block instead
+  // of being stored by the product kernel (env SPBLAS_B200_LATE_PUSH_ROWS; 0: never)
+  int64_t late_push_max_rows = 32768;
 
   // ---- host-buffer execute (spblas_b200_spmv_host, host_exec.cu) -----------------
   // The tiles cut into `host_chunks` consecutive chunks; chunk c covers tiles

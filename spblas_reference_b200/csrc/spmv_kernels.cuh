@@ -165,6 +165,9 @@ struct ScatterArgs {
   // the stream found the structure unchanged (*gate == gate_value); nullptr: no gate
   const unsigned int* gate;
   unsigned int gate_value;
+  // late push (fix-up kernel only): the rows are copied to the peers by the fix-up kernel's
+  // last block, after every carry is in, instead of being stored by the product kernel
+  int late;
 };
 
 template <typename T>
@@ -1374,7 +1377,7 @@ spmv_carry_fixup_kernel(const int64_t* __restrict__ carry_row,
         sum += carry_val[j];
       const T v = y[r] + alpha * sum;
       y[r] = v;
-      if (sc.n > 0) {
+      if (sc.n > 0 && !sc.late) {
         scatter_store(sc, r, v);
         stored_to_peer = true;
       }
@@ -1397,7 +1400,39 @@ spmv_carry_fixup_kernel(const int64_t* __restrict__ carry_row,
       bar.state[0] = 0; // ready for the next step (stream order protects it)
   }
   __syncthreads();
-  if (!s_last || int(threadIdx.x) >= bar.n)
+  if (!s_last)
+    return;
+  if (sc.late) {
+    // Late push: a few rows per peer (the halo of a banded matrix).  Stored from the product
+    // kernel they made the one CTA that owns them a straggler — measured on C2 at 4 GPUs: peer
+    // stores alone +13.5 us per step, the barrier alone +3.2 us (profiles/
+    // r02_exchange_decomposition.txt) — so the product kernel does not store them at all, and
+    // this block, which runs when every carry is in, copies them out of y (L2: other blocks
+    // wrote them) in coalesced rows.
+    __threadfence();
+    constexpr int kBatch = 8; // loads of a batch in flight together, then its peer stores
+    // (one index space over all destinations with 16 in flight measured no better: 0.2417 vs
+    // 0.2396 ms per step at 4 GPUs)
+    for (int d = 0; d < sc.n; ++d) {
+      for (int64_t base = sc.lo[d]; base < sc.hi[d]; base += int64_t(blockDim.x) * kBatch) {
+        T v[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int64_t row = base + int64_t(u) * blockDim.x + threadIdx.x;
+          v[u] = row < sc.hi[d] ? __ldcg(y + row) : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int64_t row = base + int64_t(u) * blockDim.x + threadIdx.x;
+          if (row < sc.hi[d])
+            sc.dst[d][row] = v[u];
+        }
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+  }
+  if (int(threadIdx.x) >= bar.n)
     return;
   // (st.release.sys orders everything this thread observed — the block counter's chain — before
   // the flag: no separate system fence)
@@ -1457,6 +1492,7 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
       sc.hi_max = sc.hi[d] > sc.hi_max ? sc.hi[d] : sc.hi_max;
     }
   }
+  sc.late = 0;
   BarrierArgs bar;
   bar.n = p->barrier.n;
   bar.epoch = 0;
@@ -1469,6 +1505,22 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
   }
   if (bar.n > 0)
     bar.epoch = ++p->barrier_epoch;
+  // few rows to exchange (a halo), the whole product in one launch, a barrier to hang it on:
+  // late push from the fix-up kernel; the product kernels then see no scatter at all
+  ScatterArgs<T> sc_fix = sc;
+  {
+    int64_t push_rows = 0;
+    for (int d = 0; d < sc.n; ++d)
+      push_rows += sc.hi[d] > sc.lo[d] ? sc.hi[d] - sc.lo[d] : 0;
+    const bool whole = T0 == 0 && T1 >= (variant == kVariantWarpStream || variant == kVariantHubStream ||
+                                                 variant == kVariantHubGlobal
+                                             ? p->ws_streams
+                                             : p->num_tiles);
+    if (sc.n > 0 && !sc.multicast && bar.n > 0 && whole && push_rows <= p->late_push_max_rows) {
+      sc_fix.late = 1;
+      sc.n = 0; // (lo_min / hi_max stay: wants_rows tests n first)
+    }
+  }
 
   cudaError_t e = cudaSuccess;
   // the carry arrays and the unit count of the active partition
@@ -1650,7 +1702,7 @@ int launch_spmv(spblas_b200_plan* p, int variant, const void* alpha, const void*
   const unsigned fgrid = fix_n > 0 ? unsigned((fix_n + 255) / 256) : 1u;
   if (fix_n > 0 || bar.n > 0) {
     spmv_carry_fixup_kernel<T><<<fgrid, 256, 0, p->stream>>>(
-        d_carry_row, d_carry_val, fix_lo, fix_hi, units, static_cast<T*>(y), a, sc, bar);
+        d_carry_row, d_carry_val, fix_lo, fix_hi, units, static_cast<T*>(y), a, sc_fix, bar);
     e = cudaGetLastError();
     if (e != cudaSuccess)
       return cuda_fail(p, e, "spmv_carry_fixup_kernel");
