@@ -40,6 +40,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+ALIGN_STEPS = 8        # N > 1: untimed steps queued between the host barrier and the start event
 sys.path.insert(0, ROOT)
 
 
@@ -119,6 +120,21 @@ class ClockSampler:
                     stdout=out, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def wait_first_sample(self, timeout_s=4.0):
+        """Block until nvidia-smi has written its first line: its start-up (NVML attaches to
+        every GPU of the box) must not fall into the timed region — on an 8-GPU box it cost the
+        20 timed steps 25 us each."""
+        if self.proc is None:
+            return
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < timeout_s:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.02)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -340,9 +356,18 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = info.total_launches
+        sampler.wait_first_sample()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    # N > 1: the ranks leave the host barrier tens of microseconds apart, and with the exchange
+    # fused into the kernels the first step of every rank waits for the last rank's launch — a
+    # one-off that 20 steps of 0.23 ms would carry as "per step".  ALIGN untimed steps are
+    # queued behind the barrier and ahead of the start event (no host synchronisation in
+    # between): the in-kernel flag barrier brings the GPUs into lock-step before the clock starts.
+    align = ALIGN_STEPS if world > 1 else 0
+    for _ in range(align):
+        op.step()
+    launches0 = info.total_launches
     e0.record()
     for _ in range(K):
         op.step()
@@ -503,6 +528,8 @@ def main():
                 "exchange_impl": op.exchange_impl if world > 1 else "none",
                 "exchange_calibration": getattr(op, "calibration", None),
                 "l2_policy": "inputs larger than L2 (1.34 GB per product), no flush",
+                "timed_region": (f"host barrier + synchronize, {align} untimed alignment steps queued "
+                                 f"on the stream, start event, {K} steps, stop event, synchronize + barrier"),
                 "inspect_ms": inspect_ms,
             },
             "gbs": bytes_launch * world / (step_ms * 1e-3) / 1e9,

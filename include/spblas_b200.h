@@ -336,6 +336,10 @@ SPBLAS_B200_API int spblas_b200_transpose(spblas_b200_plan* plan, int val_type,
      row 0 lives in destination d's next x (peer's base + r0).  With
      multicast != 0 the addresses are NVLS multicast addresses and the stores
      are multimem.st (one store reaches every GPU).  n_dst = 0 switches it off.
+     When the ranges hold few rows in total (a halo: at most
+     SPBLAS_B200_LATE_PUSH_ROWS, default 32768) and a barrier is set, the rows are
+     copied out of y by the carry fix-up kernel's last block instead of being stored
+     by the product kernels (the CTA that owned them was a straggler).
    set_barrier: every spblas_b200_spmv on this plan ends with a flag barrier
      among the ranks: d_remote_slots[q] is this rank's slot in peer q's flag
      array (peer-mapped), d_local_slots[q] the slot peer q writes here; flags
