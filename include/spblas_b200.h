@@ -170,8 +170,8 @@ SPBLAS_B200_API int spblas_b200_plan_cache_values(spblas_b200_plan* plan, int va
    is bound by the gathers of x that miss L1, not by HBM.  With enable != 0, a plan that
    would run the general (warp-stream) SpMV kernel counts the references per column on
    its first product, keeps the columns referenced at least min_count times (0 = twice
-   the SM count), takes the max_cols most referenced of them (0 = 32768 4-byte or 12288 8-byte
-   values: a 164 KB shared-memory carve-out, which leaves L1 the 92 KB the gathers in
+   the SM count), takes the max_cols most referenced of them (0 = 32768 4-byte or 8192 8-byte
+   values: a 164 / 131 KB shared-memory carve-out, which leaves L1 what the gathers in
    flight need; at most 49152 / 20480, what the SM's shared memory holds)
    and stores a re-encoded copy of colind (nnz * 4 bytes, owned by the plan); the hub
    kernel then reads x at those columns from shared memory.  Used only if at least 15 %

@@ -112,7 +112,11 @@ struct Scratch { // freed when the analysis returns, however it returns
 // of shared memory, because every gather in flight occupies an L1 line and L1 is what
 // shared memory leaves of the SM's unified array: on R-MAT scale 24 (fp32) 32768 columns
 // (160 KB) run in 1.03 ms, 40960 (192 KB) in 1.08 ms, 49152 (224 KB) in 1.76 ms — slower
-// than no table at all (1.13 ms).  Whole 1024-column steps.
+// than no table at all (1.13 ms).  With the walk's branch-free load phase (eight gathers in
+// flight per lane instead of four) the optimum moved towards a larger L1
+// (profiles/r02_hub_sweep_flat.jsonl): fp32 24576 / 32768 columns 0.971 / 0.975 ms, 40960
+// 1.128; fp64 (R-MAT scale 24) 8192 columns 1.231 ms, 12288 1.334, 16384 1.706 — the
+// 8-byte default is 8192 columns (131 KB of shared memory).  Whole 1024-column steps.
 int64_t hub_capacity(const spblas_b200_plan* p, size_t val_bytes, int walk_warps) {
   const int64_t slabs = int64_t(walk_warps) * 256 * int64_t(val_bytes);
   const auto columns = [&](int64_t budget) {
@@ -122,7 +126,7 @@ int64_t hub_capacity(const spblas_b200_plan* p, size_t val_bytes, int walk_warps
   const int64_t hw = columns(int64_t(p->smem_per_sm) - 1024); // per-CTA limit: 1 KB is the system's
   if (p->hub_cap_override > 0)
     return p->hub_cap_override < hw ? p->hub_cap_override : hw;
-  return std::min(hw, columns(int64_t(163) * 1024));
+  return std::min(hw, columns(int64_t(val_bytes == 8 ? 131 : 163) * 1024));
 }
 
 // How many columns the GLOBAL-memory table holds (spmv_hubg_stream_kernel): half of L2 —

@@ -67,7 +67,7 @@ int prepare_spmv(spblas_b200_plan* p, int val_type, const void* values, int* var
     const int64_t resident =
         v == kVariantHubStream
             ? int64_t(p->num_sms) * kHubWarps
-            : int64_t(p->num_sms) * (wide ? kWsCtasPerSm - 1 : kWsCtasPerSm) * kWsWarps;
+            : int64_t(p->num_sms) * (wide ? kWsCtasPerSmWide : kWsCtasPerSm) * kWsWarps;
     if (int rc = build_ws_partition(p, resident))
       return rc;
   }

@@ -777,11 +777,21 @@ spmv_pipe_kernel(const O* __restrict__ rowptr, const I* __restrict__ colind,
 // stream's trailing partial row is a carry, added by the same fix-up kernel.
 constexpr int kWsChunk = 256;   // nonzeros per warp step
 constexpr int kWsWarps = 8;     // warps per CTA
-constexpr int kWsCtasPerSm = 6; // 48 warps per SM (40 with 8-byte values or indices)
+// CTAs per SM = the register budget of the walk: 5 -> 48 registers, 4 -> 64.  With all of a
+// chunk's loads issued together (kWsFlat) 40 registers (6 CTAs) spill; build-time switches for
+// the A/B runs (profiles/r02_flat_walk_ab.jsonl).
+#ifndef B200_WS_CTAS
+#define B200_WS_CTAS 5
+#endif
+#ifndef B200_WS_CTAS_WIDE
+#define B200_WS_CTAS_WIDE 4
+#endif
+constexpr int kWsCtasPerSm = B200_WS_CTAS;          // 4-byte values and indices
+constexpr int kWsCtasPerSmWide = B200_WS_CTAS_WIDE; // 8-byte values or indices
 
 template <typename T, typename I>
 constexpr int ws_ctas_per_sm() {
-  return (sizeof(T) == 8 || sizeof(I) == 8) ? kWsCtasPerSm - 1 : kWsCtasPerSm;
+  return (sizeof(T) == 8 || sizeof(I) == 8) ? kWsCtasPerSmWide : kWsCtasPerSm;
 }
 
 // The walk of one warp over its streams, shared by the two kernels below.  HUB: `colind`
@@ -840,6 +850,43 @@ __device__ __forceinline__ T ws_gather(const T* p) {
     return ld_ro(p);
 }
 
+// one gather of x for the walk.  HUB 0: through L1; HUB 1: a negative index reads the
+// shared-memory table, the rest bypass L1; HUB 2: a negative index reads the compact table
+// in global memory.  L1 policy of HUB 2 (build-time switch B200_HUBG_L1, measured on the
+// scale-27 shard, profiles/r02_hubg_l1_priorities.jsonl): 0 one plain load either way
+// 1.92 ms; 1 table lines evict_last 1.88 ms; 2 (default) table evict_last AND the cold
+// gathers of x not allocated in L1 — they come from DRAM and would only push the table's
+// lines out — 1.69 ms; 3 cold gathers evict_first 1.73 ms.
+template <int HUB, typename T, typename I>
+__device__ __forceinline__ T ws_gather_x(const T* __restrict__ x, const T* __restrict__ xh,
+                                         const uint32_t hub, const I c) {
+  if constexpr (HUB == 1) {
+    return c < I(0) ? ld_hub<T>(hub, int(~c)) : ws_gather<true>(x + c);
+  } else if constexpr (HUB == 2) {
+    const bool h = c < I(0);
+#if defined(B200_HUBG_L1) && B200_HUBG_L1 == 0
+    return ld_ro((h ? xh : x) + (h ? ~c : c));
+#elif defined(B200_HUBG_L1) && B200_HUBG_L1 == 1
+    return h ? ld_ro_l1_evict_last(xh + ~c) : ld_ro(x + c);
+#elif defined(B200_HUBG_L1) && B200_HUBG_L1 == 3
+    return h ? ld_ro(xh + ~c) : ld_ro_l1_evict_first(x + c);
+#else
+    if constexpr (kHubgL2)
+      return h ? ld_ro_keep(xh + ~c) : ld_stream_ef(x + c);
+    else
+      return h ? ld_ro_l1_evict_last(xh + ~c) : ld_stream(x + c);
+#endif
+  } else {
+    return ws_gather<false>(x + c);
+  }
+}
+
+// B200_WS_FLAT=0 builds the walk without the branch-free load phase (A/B runs only)
+#ifndef B200_WS_FLAT
+#define B200_WS_FLAT 1
+#endif
+constexpr bool kWsFlat = B200_WS_FLAT != 0;
+
 template <typename T, typename I, typename O, int HUB, int WARPS, bool ADD>
 __device__ __forceinline__ void
 ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
@@ -881,74 +928,99 @@ ws_walk_streams(const O* __restrict__ rowptr, const I* __restrict__ colind,
     do {
       const int kend = kb + kWsChunk < k_e ? kb + kWsChunk : k_e;
       // ---- products of this chunk: two quads per lane -----------------------------
+      constexpr bool kEF = kWsStreamEF || (HUB == 2 && kHubgL2);
       T p[2][4];
+      int re = 0x7fffffff;
+      if (kWsFlat && kb + kWsChunk <= arr_end) {
+        // Every quad of the chunk lies inside the arrays (all chunks but the arrays' last):
+        // the loads need no bounds, so ALL of them — both quads of colind and of values, the
+        // row ends, then the eight gathers — are issued from one basic block before anything
+        // waits.  Written with a branch around each quad (the general form below) the
+        // compiler keeps the quads apart: colind -> gathers -> products of quad 0, only then
+        // the loads of quad 1, then the row ends: five memory latencies in a row per chunk
+        // and four gathers in flight per lane instead of two latencies and eight.  A lane
+        // whose quad lies outside [k, kend) reads the chunk's first quad instead (one address
+        // for all such lanes: a broadcast, no extra sectors) and its products are zeroed.
+        Quad<I> c[2];
+        Quad<T> v[2];
+        int kq[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int kk = kb + 4 * (lane + 32 * u);
+        for (int u = 0; u < 2; ++u) {
+          const int kk = kb + 4 * (lane + 32 * u);
+          kq[u] = (kk < kend && kk + 4 > k) ? kk : kb;
+          c[u] = ld_stream_quad_p<kEF>(ci + kq[u]);
+        }
+        if (lane < rows_left)
+          re = int(int64_t(ld_stream_p<kEF>(rowptr + row + 1 + lane)) - base);
+        if (!has_perm) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          p[u][j] = T(0);
-        if (kk < kend && kk + 4 > k) {
-          Quad<I> c;
-          Quad<T> v;
-          if (kk + 4 <= arr_end) {
-            c = ld_stream_quad_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(ci + kk);
-            if (!has_perm) {
-              v = ld_stream_quad_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(va + kk);
-            } else {
-              const Quad<O> pi = ld_stream_quad_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(perm + base + kk);
+          for (int u = 0; u < 2; ++u)
+            v[u] = ld_stream_quad_p<kEF>(va + kq[u]);
+        } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                v.v[j] = ld_ro(values + pi.v[j]);
-            }
-          } else { // the arrays' last partial quad
+          for (int u = 0; u < 2; ++u) {
+            const Quad<O> pi = ld_stream_quad_p<kEF>(perm + base + kq[u]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const bool in = kk + j < arr_end;
-              c.v[j] = in ? ld_stream_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(ci + kk + j) : I(0);
-              v.v[j] = !in ? T(0)
-                           : (has_perm ? ld_ro(values + perm[base + kk + j])
-                                       : ld_stream_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(va + kk + j));
-            }
+            for (int j = 0; j < 4; ++j)
+              v[u].v[j] = ld_ro(values + pi.v[j]);
           }
-          T xv[4];
+        }
+        T xv[2][4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if constexpr (HUB == 1) {
-              xv[j] = c.v[j] < I(0) ? ld_hub<T>(hub, int(~c.v[j])) : ws_gather<true>(x + c.v[j]);
-            } else if constexpr (HUB == 2) {
-              // a negative index reads the compact table.  L1 policy (build-time switch
-              // B200_HUBG_L1, measured on the scale-27 shard, profiles/
-              // r02_hubg_l1_priorities.jsonl): 0 one plain load either way 1.92 ms; 1 table
-              // lines evict_last 1.88 ms; 2 (default) table evict_last AND the cold gathers of
-              // x not allocated in L1 — they come from DRAM and would only push the table's
-              // lines out — 1.69 ms; 3 cold gathers evict_first 1.73 ms.
-              const bool h = c.v[j] < I(0);
-#if defined(B200_HUBG_L1) && B200_HUBG_L1 == 0
-              xv[j] = ld_ro((h ? xh : x) + (h ? ~c.v[j] : c.v[j]));
-#elif defined(B200_HUBG_L1) && B200_HUBG_L1 == 1
-              xv[j] = h ? ld_ro_l1_evict_last(xh + ~c.v[j]) : ld_ro(x + c.v[j]);
-#elif defined(B200_HUBG_L1) && B200_HUBG_L1 == 3
-              xv[j] = h ? ld_ro(xh + ~c.v[j]) : ld_ro_l1_evict_first(x + c.v[j]);
-#else
-              if constexpr (kHubgL2)
-                xv[j] = h ? ld_ro_keep(xh + ~c.v[j]) : ld_stream_ef(x + c.v[j]);
-              else
-                xv[j] = h ? ld_ro_l1_evict_last(xh + ~c.v[j]) : ld_stream(x + c.v[j]);
-#endif
-            } else {
-              xv[j] = ws_gather<false>(x + c.v[j]);
-            }
-          }
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            p[u][j] = (kk + j >= k && kk + j < kend) ? v.v[j] * xv[j] : T(0);
+            xv[u][j] = ws_gather_x<HUB, T, I>(x, xh, hub, c[u].v[j]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int kk = kb + 4 * (lane + 32 * u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            p[u][j] = (kk + j >= k && kk + j < kend) ? v[u].v[j] * xv[u][j] : T(0);
         }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int kk = kb + 4 * (lane + 32 * u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            p[u][j] = T(0);
+          if (kk < kend && kk + 4 > k) {
+            Quad<I> c;
+            Quad<T> v;
+            if (kk + 4 <= arr_end) {
+              c = ld_stream_quad_p<kEF>(ci + kk);
+              if (!has_perm) {
+                v = ld_stream_quad_p<kEF>(va + kk);
+              } else {
+                const Quad<O> pi = ld_stream_quad_p<kEF>(perm + base + kk);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  v.v[j] = ld_ro(values + pi.v[j]);
+              }
+            } else { // the arrays' last partial quad
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const bool in = kk + j < arr_end;
+                c.v[j] = in ? ld_stream_p<kEF>(ci + kk + j) : I(0);
+                v.v[j] = !in ? T(0)
+                             : (has_perm ? ld_ro(values + perm[base + kk + j])
+                                         : ld_stream_p<kEF>(va + kk + j));
+              }
+            }
+            T xv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              xv[j] = ws_gather_x<HUB, T, I>(x, xh, hub, c.v[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              p[u][j] = (kk + j >= k && kk + j < kend) ? v.v[j] * xv[j] : T(0);
+          }
+        }
+        // ---- rows that end inside the chunk -----------------------------------------
+        if (lane < rows_left)
+          re = int(int64_t(ld_stream_p<kEF>(rowptr + row + 1 + lane)) - base);
       }
-      // ---- rows that end inside the chunk -------------------------------------------
-      int re = 0x7fffffff;
-      if (lane < rows_left)
-        re = int(int64_t(ld_stream_p<kWsStreamEF || (HUB == 2 && kHubgL2)>(rowptr + row + 1 + lane)) - base);
       unsigned mask = __ballot_sync(0xffffffffu, re <= kend);
       if (mask == 0u) {
         // the chunk lies inside one row: no shared memory, straight to the shuffle tree

@@ -245,7 +245,7 @@ def test_hub_automatic_choice(cuda, oracle):
 
 def test_hub_default_capacity_and_value_width_switch(cuda, oracle, monkeypatch):
     """Default limits on a matrix large enough to fill the table: 32768 columns for 4-byte
-    values, 12288 for 8-byte ones (a 164 KB carve-out; L1 keeps the rest); the table is
+    values (a 164 KB carve-out), 8192 for 8-byte ones (131 KB); L1 keeps the rest; the table is
     rebuilt when the value width changes; an explicit max_cols may go up to what the SM's
     shared memory holds (49152 / 20480)."""
     # (the stream length follows the number of resident warps, which differs between the two
@@ -269,8 +269,8 @@ def test_hub_default_capacity_and_value_width_switch(cuda, oracle, monkeypatch):
     y64 = torch.empty(m, dtype=torch.float64, device=cuda)
     sb.multiply_execute(info, a64, x64, y64)
     torch.cuda.synchronize()
-    hubs64, refs64, enc64 = oracle.hub_columns(ci, n, 12288, 8)
-    assert info.spmv_variant == 3 and info.hub_count == 12288 and info.hub_refs == refs64
+    hubs64, refs64, enc64 = oracle.hub_columns(ci, n, 8192, 8)
+    assert info.spmv_variant == 3 and info.hub_count == 8192 and info.hub_refs == refs64
     assert np.array_equal(info.hub_cols, hubs64) and np.array_equal(info.hub_colind, enc64)
     y_ref = oracle.spmv("csr", (m, n), rp, ci, v.astype(np.float64), x.astype(np.float64))
     assert_rows_within_bound(y64.cpu().numpy(), y_ref, rp,
