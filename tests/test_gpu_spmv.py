@@ -428,3 +428,56 @@ def test_pipe_kernel_ragged_last_tile_every_stage_count(cuda, oracle, monkeypatc
                 assert info.spmv_variant == 1
                 assert np.array_equal(y.cpu().numpy(), want), (uniform, tail, stages, rep)
             info.close()
+
+
+@pytest.mark.parametrize("ws_items", ["256", "1024", "0"])
+@pytest.mark.parametrize("variant", [2, 3, 4])
+def test_walk_lanes_outside_their_stream_contribute_nothing(cuda, oracle, monkeypatch, variant,
+                                                            ws_items):
+    """The walk's branch-free load phase lets a lane whose quad lies outside [k, kend) of its
+    stream load the chunk's first quad instead (entries of ANOTHER stream's rows) and zeroes
+    its products.  x holds NaN at columns that only one marked row references: if a product
+    taken outside a lane's own range leaked — or were multiplied by zero instead of being
+    dropped — a second row would turn NaN.  Streams of 256 / 1024 entries start and end in the
+    middle of chunks and of rows; variants 3 and 4 read the hub tables (re-encoded colind)."""
+    monkeypatch.setenv("SPBLAS_B200_SPMV_VARIANT", str(variant))
+    if ws_items != "0":
+        monkeypatch.setenv("SPBLAS_B200_WS_ITEMS", ws_items)
+    rng = np.random.default_rng(100 + variant)
+    m, n = 6007, 5000
+    n_clean = 4000                                   # columns 4000.. are referenced by marked rows only
+    lens = rng.integers(0, 40, m)
+    lens[rng.integers(0, m, 12)] = rng.integers(300, 900, 12)      # rows spanning several chunks
+    marked = np.sort(rng.choice(m, 25, replace=False))
+    rp = np.zeros(m + 1, np.int32)
+    np.cumsum(lens, out=rp[1:])
+    # skewed columns so that hub tables form (variants 3 / 4 keep them only if they pay)
+    ci = np.minimum((n_clean * rng.random(rp[-1]) ** 3).astype(np.int32), n_clean - 1)
+    v = rng.standard_normal(rp[-1])
+    x = rng.standard_normal(n)
+    for t, r in enumerate(marked):
+        if lens[r] == 0:
+            continue
+        ci[rp[r] + rng.integers(0, lens[r])] = n_clean + t          # one private column each
+        x[n_clean + t] = np.nan
+    for vt in (np.float32, np.float64):
+        a = csr_on_device(v.astype(vt), rp, ci, (m, n))
+        xd = dev(x.astype(vt))
+        info = sb.multiply_inspect(a, xd, torch.empty(m, dtype=xd.dtype, device="cuda"))
+        if variant >= 3:
+            info.set_hub(True, 2048, 2)
+            info.force_spmv_variant(variant)
+        y = gpu_spmv(a, x.astype(vt), m, vt, info=info)
+        assert info.spmv_variant == variant
+        expect_nan = np.zeros(m, bool)
+        expect_nan[marked[lens[marked] > 0]] = True
+        assert np.array_equal(np.isnan(y), expect_nan), \
+            f"variant {variant}: NaN rows {np.flatnonzero(np.isnan(y) != expect_nan)[:8]}"
+        xz = np.where(np.isnan(x), 0.0, x).astype(vt)
+        y_ref = oracle.spmv("csr", (m, n), rp, ci, v.astype(vt), xz)
+        ok = ~expect_nan
+        bound = oracle.abs_rowsum(rp, ci, v.astype(vt), xz)
+        err = np.abs(y.astype(np.float64) - y_ref)[ok]
+        tol = ((lens + 2) * (2.0 ** -23 if vt == np.float32 else 2.0 ** -52) * bound)[ok]
+        assert (err <= tol).all(), f"variant {variant} {vt.__name__}: max err/tol {np.max(err / np.maximum(tol, 1e-300))}"
+        info.close()
