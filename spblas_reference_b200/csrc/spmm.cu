@@ -842,6 +842,23 @@ int launch_spmm(spblas_b200_plan* p, const T alpha, const void* values,
   return SPBLAS_B200_SUCCESS;
 }
 
+// Does a fair share of the stored entries sit in long rows?  Lower bound from the inspect
+// phase's log2 row-length histogram (bin b holds the rows of 2^(b-1) .. 2^b - 1 entries): the
+// entries of rows with at least 256.  On such a matrix the group kernel — one group of lanes
+// per row, rows of up to 4096 entries walked by a single group — leaves most lanes waiting for
+// the groups that drew the long rows, and the stream kernel, whose merge-path runs cut rows
+// wherever the work is, wins at EVERY width of B (R-MAT scale 22, profiles/
+// r02_spmm_rmat_narrow.jsonl: fp32 k = 8 / 16 / 32 6.2 / 9.4 / 10.5 ms -> 2.9 / 2.9 / 2.8 ms,
+// fp64 k = 4 / 16 6.8 / 11.9 -> 3.5 / 3.5 ms).
+bool heavy_tailed_rows(const spblas_b200_plan* p) {
+  if (!p->have_hist || p->nnz <= 0)
+    return false;
+  double in_long_rows = 0.0;
+  for (int b = 9; b < SPBLAS_B200_HIST_BINS; ++b)
+    in_long_rows += double(p->hist[b]) * double(1ull << (b - 1));
+  return in_long_rows >= 0.10 * double(p->nnz);
+}
+
 // One pass: C[:, 0:k] = alpha * A * B[:, 0:k] for the k columns starting at B / C.
 template <typename T, typename I, typename O>
 int spmm_pass(spblas_b200_plan* p, const void* alpha, const void* values,
@@ -857,11 +874,13 @@ int spmm_pass(spblas_b200_plan* p, const void* alpha, const void* values,
   // Stream kernel when a row of B is at least kRingMinRowBytes long: there it reaches
   // the DRAM peak on its traffic (C3 k=128: 6.4 TB/s), while on 128-byte rows both
   // kernels sit at the same random-access DRAM ceiling (~4.3 TB/s) and the group kernel
-  // spends fewer instructions.  B's row pitch must fit 32 bits, <= 65535 column tiles.
+  // spends fewer instructions — unless the row lengths are heavy-tailed (the inspect phase's
+  // histogram decides: heavy_tailed_rows).  B's row pitch must fit 32 bits, <= 65535 column tiles.
   const bool ring_ok = ldb * int64_t(sizeof(T)) < (int64_t(1) << 31) && k <= 65535 * 32;
   const bool ring = p->spmm_forced >= 0
                         ? (p->spmm_forced == 1 && ring_ok)
-                        : (ring_ok && k * int64_t(sizeof(T)) >= kRingMinRowBytes);
+                        : (ring_ok && (k * int64_t(sizeof(T)) >= kRingMinRowBytes ||
+                                       heavy_tailed_rows(p)));
   if (ring) {
     constexpr int S = int(sizeof(T));
     // 16-byte granules need 16-byte aligned rows of B (C may be anywhere unless the

@@ -176,3 +176,32 @@ def test_spmm_both_kernels_every_width(cuda, oracle, monkeypatch, variant, k, vt
     sb.multiply_execute(info, sb.scaled(0.5, a), Bd, C2)
     assert torch.equal(C2, Cd)
     info.close()
+
+
+def test_row_length_histogram_steers_the_narrow_spmm(cuda, oracle):
+    """A narrow B (rows of B shorter than 256 bytes) takes the group-per-row kernel on a matrix
+    with even row lengths and the merge-path stream kernel when the inspect phase's row-length
+    histogram says that >= 10 % of the entries sit in rows of >= 256 entries (a power-law
+    matrix: 2-4x faster there, profiles/r02_spmm_rmat_narrow.jsonl).  Both within the bound."""
+    rng = np.random.default_rng(77)
+    m, n, k = 6000, 5000, 8
+    for heavy in (False, True):
+        lens = rng.integers(0, 24, size=m)
+        if heavy:
+            lens[rng.choice(m, 40, replace=False)] = rng.integers(300, 3000, 40)
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        nnz = int(rp[-1])
+        ci = rng.integers(0, n, size=nnz).astype(np.int32)
+        v = rng.standard_normal(nnz).astype(np.float32)
+        B = rng.standard_normal((n, k)).astype(np.float32)
+        a = csr_on_device(v, rp, ci, (m, n))
+        Bd = dev(B)
+        Cd = torch.full((m, k), float("nan"), dtype=Bd.dtype, device="cuda")
+        info = sb.multiply_inspect(a, Bd, Cd)
+        sb.multiply_execute(info, a, Bd, Cd)
+        torch.cuda.synchronize()
+        assert (info.spmm_variant >= 1000) == heavy, (heavy, info.spmm_variant)
+        C_ref = oracle.spmm("csr", (m, n), rp, ci, v, B)
+        assert_rows_within_bound(Cd.cpu().numpy(), C_ref, rp, spmm_bound(rp, ci, v, B),
+                                 f"histogram-steered SpMM heavy={heavy}")
+        info.close()
