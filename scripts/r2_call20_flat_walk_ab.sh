@@ -1,7 +1,10 @@
 #!/bin/bash
 # A/B of the walk's branch-free load phase (B200_WS_FLAT) and its register budget
 # (B200_WS_CTAS / _WIDE): old = round-2 production (FLAT=0, 6/5 CTAs per SM), base = the shipped build =
-# FLAT=1 5/4, f65 = FLAT=1 6/5 (spills), f43 = FLAT=1 4/3.
+# FLAT=1 5/4, f65 = FLAT=1 6/5 (spills), f43 = FLAT=1 4/3.  The A/B builds are made with
+#   make -C spblas_reference_b200/csrc OUT=../libspblas_b200_<name>.so OBJDIR=../../build/obj_<name> \
+#        EXTRA="-DB200_WS_FLAT=<0|1> -DB200_WS_CTAS=<n> -DB200_WS_CTAS_WIDE=<n>"
+# and are not kept in the tree (30 MB each).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 out=gpurun_out/r2_flat_walk_ab.jsonl; : > $out

@@ -2,6 +2,9 @@
 # The hub kernel with cp.async landing zones (spmv_hubl_stream_kernel, SPBLAS_B200_HUB_LANDING=1):
 # parity (the hub suites with the env set), then timing against the LDG hub kernel on C4 (fp32)
 # and R-MAT scale 24 fp64, over table sizes and warps per CTA (hw24/hw32 builds).
+# Kept as the record of how profiles/r02_hub_landing_negative.jsonl was produced: the kernel, its
+# environment switch and the hw24/hw32 builds were REMOVED after this run (slower at every shape;
+# DESIGN 4.13) — the script no longer runs against the current library.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 out=gpurun_out/r2_hub_landing.jsonl; : > $out
