@@ -29,15 +29,27 @@ def _stream_ptr(device) -> int:
     return int(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _destroy_plan(plan):
+    _cabi.lib().spblas_b200_plan_destroy(plan)
+
+
 class operation_info_t:
     """Result of multiply_inspect: owns the backend plan (RAII, move-only in C++:
     include/spblas/vendor/b200/operation_state_t.hpp).  result_shape / result_nnz mirror
     detail/operation_info_t.hpp:30-36."""
 
+    # One info may be inspected for more than one operand: the reference's notes inspect `a`
+    # and `transposed(a)` with ONE operation_info_t and alternate the executes
+    # (notes/spmv.hpp:12-22).  The current structure's plan is `_plan` / `_sig`; up to
+    # _MAX_PARKED other structures keep their own plan, so that alternating executes switch
+    # plans instead of re-inspecting (a CSC operand's inspect sorts the whole image).
+    _MAX_PARKED = 3
+
     def __init__(self):
         self._plan = C.c_void_p()
         self._device = None
         self._sig = None
+        self._parked = []            # [(sig, plan handle, device)], most recently used last
         self.result_shape = (0, 0)
         self.result_nnz = 0
 
@@ -50,11 +62,45 @@ class operation_info_t:
             self._device = device
         return self._plan
 
+    def _select(self, sig) -> bool:
+        """Make the plan inspected for `sig` the current one; False if there is none."""
+        if self._plan and self._sig == sig:
+            return True
+        for i, (s, plan, device) in enumerate(self._parked):
+            if s == sig:
+                del self._parked[i]
+                self._park()
+                self._plan, self._sig, self._device = plan, s, device
+                return True
+        return False
+
+    def _park(self):
+        """Set the current plan aside (its structure stays inspected) so that the next
+        _ensure() creates a fresh one; the least recently used parked plan makes room."""
+        if not self._plan:
+            return
+        if self._sig is None:        # never inspected: nothing worth keeping, reuse it
+            return
+        self._parked.append((self._sig, self._plan, self._device))
+        self._plan, self._sig = C.c_void_p(), None
+        while len(self._parked) > self._MAX_PARKED:
+            _, old, _ = self._parked.pop(0)
+            _destroy_plan(old)
+
+    def _begin_inspect(self, sig):
+        """Called by every inspect: reuse the plan of the same structure (a re-inspect),
+        else park the current one."""
+        if not self._select(sig):
+            self._park()
+
     def close(self):
         if self._plan:
-            _cabi.lib().spblas_b200_plan_destroy(self._plan)
+            _destroy_plan(self._plan)
             self._plan = C.c_void_p()
             self._sig = None
+        for _, plan, _ in self._parked:
+            _destroy_plan(plan)
+        self._parked = []
 
     def __del__(self):
         try:
@@ -225,6 +271,7 @@ def _inspect(info: operation_info_t, a, x, y, flags=_cabi.INSPECT_DEFAULT):
     x_base = get_ultimate_base(x)
     _check_shapes(a_base, x_base, y)
     dev = a_base.values.device
+    info._begin_inspect(_signature(fmt, a_base, ptr, ind))
     plan = info._ensure(dev)
     k_hint = int(y.shape[1]) if _is_matrix(y) else 1
     with torch.cuda.device(dev):
@@ -339,8 +386,8 @@ def _execute(info: Optional[operation_info_t], a, x, y, d=None):
             _cabi.raise_for_status(st, L.spblas_b200_last_error_once().decode())
             return
 
-        if info._sig != _signature(fmt, a_base, ptr, ind):
-            # first use of this info, or a different matrix: inspect lazily, like
+        if not info._select(_signature(fmt, a_base, ptr, ind)):
+            # first use of this info for this matrix: inspect lazily, like
             # vendor/cusparse/spmv_impl.hpp:43-55 creates its state on first use
             _inspect(info, a, x, y)
         plan = info._plan
@@ -420,7 +467,7 @@ def multiply_execute_host(info: operation_info_t, a, x_host: torch.Tensor, y_hos
     dev = a_base.values.device
     m, n = a_base.shape
     with torch.cuda.device(dev):
-        if info._sig != _signature(fmt, a_base, ptr, ind):
+        if not info._select(_signature(fmt, a_base, ptr, ind)):
             _inspect(info, a, torch.empty(n, dtype=x_base.dtype, device=dev),
                      torch.empty(m, dtype=x_base.dtype, device=dev))
         stage = getattr(info, "_stage", None)

@@ -47,6 +47,7 @@ def _sig(a):
 def _inspect(info: operation_info_t, a, b):
     a, b = _check(a, b)
     dev = a.values.device
+    info._begin_inspect(_sig(a))
     plan = info._ensure(dev)
     with torch.cuda.device(dev):
         _cabi.lib().spblas_b200_plan_set_stream(plan, _stream_ptr(dev))
@@ -83,7 +84,7 @@ def transpose(*args):
     else:
         raise TypeError("transpose(a, b) or transpose(info, a, b)")
     a_base, b_base = _check(a, b)
-    if info._sig != _sig(a_base):
+    if not info._select(_sig(a_base)):
         _inspect(info, a_base, b_base)
     dev = a_base.values.device
     with torch.cuda.device(dev):

@@ -89,6 +89,7 @@ def _sig(a_base, uplo, diag):
 def _inspect(info: operation_info_t, a, uplo, diag, b, x):
     a_base, _ = _decode(a, uplo, diag, b, x)
     dev = a_base.values.device
+    info._begin_inspect(_sig(a_base, uplo, diag))
     plan = info._ensure(dev)
     with torch.cuda.device(dev):
         _cabi.lib().spblas_b200_plan_set_stream(plan, _stream_ptr(dev))
@@ -126,7 +127,7 @@ def triangular_solve(*args):
         raise TypeError("triangular_solve(a, uplo, diag, b, x) or (info, a, uplo, diag, b, x)")
     a, uplo, diag, b, x = rest
     a_base, b_base = _decode(a, uplo, diag, b, x)
-    if info._sig != _sig(a_base, uplo, diag):
+    if not info._select(_sig(a_base, uplo, diag)):
         _inspect(info, a, uplo, diag, b, x)
     vt = value_type(a_base.values)
     if vt == _cabi.S32:

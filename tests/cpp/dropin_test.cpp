@@ -270,6 +270,64 @@ void csc_cases() {
   }
 }
 
+// ---- one info, two operands: the alternating loop of the reference's notes ---------------------
+// notes/spmv.hpp:12-22: multiply_inspect(info, a, x, y); multiply_inspect(info, transposed(a),
+// y, x); then multiply_execute(info, a, x, y) and multiply_execute(info, transposed(a), y, x) in
+// turn.  The info keeps one plan per inspected structure: the executes switch plans, they do
+// not re-inspect (the plan pointers seen by the two operands never change).
+void alternating_case() {
+  using T = double;
+  using I = spblas::index_t;
+  using O = spblas::offset_t;
+  const int m = 300, n = 200, nnz = 4000;
+  auto [values, rowptr, colind, shape, nnz_] = spblas::generate_csr<T, I, O>(m, n, nnz);
+  for (auto& v : values)
+    v = T(0.01) * v; // keeps the iterates small
+  device_array<T> d_values(values);
+  device_array<O> d_rowptr(rowptr);
+  device_array<I> d_colind(colind);
+  std::vector<T> x(n);
+  for (int j = 0; j < n; ++j)
+    x[j] = T(1 + j % 5);
+  device_array<T> d_x(x), d_y(m, T(-1));
+  spblas::csr_view<T, I, O> a(d_values.get(), d_rowptr.get(), d_colind.get(), shape, O(nnz));
+  std::span<T> xs(d_x.get(), n), ys(d_y.get(), m);
+  g_case = "alternating A x / A^T y with one info";
+  spblas::operation_info_t info;
+  spblas::multiply_inspect(info, a, xs, ys);
+  spblas_b200_plan* plan_a = info.state_.plan();
+  spblas::multiply_inspect(info, spblas::transposed(a), ys, xs);
+  spblas_b200_plan* plan_at = info.state_.plan();
+  ++g_checks;
+  if (plan_a == nullptr || plan_at == nullptr || plan_a == plan_at)
+    fail("the two operands must own two plans");
+  for (int it = 0; it < 3; ++it) {
+    spblas::multiply_execute(info, a, xs, ys);
+    ++g_checks;
+    if (info.state_.plan() != plan_a)
+      fail("execute on a re-inspected or replaced plan (A)");
+    std::vector<T> y_ref = host_spmv<T, I, O>(m, rowptr, colind, values, x, T(1));
+    expect_all_close(y_ref, d_y.to_host());
+    spblas::multiply_execute(info, spblas::transposed(a), ys, xs);
+    ++g_checks;
+    if (info.state_.plan() != plan_at)
+      fail("execute on a re-inspected or replaced plan (A^T)");
+    std::vector<T> x_ref(n, T(0));
+    for (int i = 0; i < m; ++i)
+      for (O p = rowptr[i]; p < rowptr[i + 1]; ++p)
+        x_ref[colind[p]] += values[p] * y_ref[i];
+    expect_all_close(x_ref, d_x.to_host());
+    x = x_ref;
+  }
+  // a moved info takes every plan with it
+  spblas::operation_info_t moved = std::move(info);
+  spblas::multiply_execute(moved, a, xs, ys);
+  ++g_checks;
+  if (moved.state_.plan() != plan_a || info.state_.plan() != nullptr)
+    fail("move must carry the parked plans");
+  expect_all_close(host_spmv<T, I, O>(m, rowptr, colind, values, x, T(1)), d_y.to_host());
+}
+
 // ---- SpMM ---------------------------------------------------------------------------------------
 template <typename T>
 void spmm_cases() {
@@ -558,6 +616,7 @@ int main() {
   spmv_cases<double, std::int32_t, std::int64_t>();
   spmv_cases<float, std::int64_t, std::int64_t>();
   csc_cases();
+  alternating_case();
   spmm_cases<float>();
   spmm_cases<double>();
   csc_spmm_case();

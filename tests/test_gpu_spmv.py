@@ -481,3 +481,44 @@ def test_walk_lanes_outside_their_stream_contribute_nothing(cuda, oracle, monkey
         tol = ((lens + 2) * (2.0 ** -23 if vt == np.float32 else 2.0 ** -52) * bound)[ok]
         assert (err <= tol).all(), f"variant {variant} {vt.__name__}: max err/tol {np.max(err / np.maximum(tol, 1e-300))}"
         info.close()
+
+
+def test_alternating_a_and_transposed_a_with_one_info(cuda, oracle, monkeypatch):
+    """The reference's flagship iterative use (notes/spmv.hpp:12-22): ONE operation_info_t is
+    inspected for `a` and for `transposed(a)`, then the executes alternate.  The info keeps a
+    plan per structure: after the two inspects no execute inspects again, and every product is
+    within the bound of the reference's CPU multiply on the same input."""
+    import sys
+    M = sys.modules["spblas_reference_b200.multiply"]
+    rng = np.random.default_rng(2024)
+    m, n = 3001, 2500
+    v, rp, ci, _ = _random_csr(rng, m, n, "mixed", np.float64, np.int32, np.int32)
+    v = v * 0.05
+    a = csr_on_device(v, rp, ci, (m, n))
+    at = sb.transposed(a)
+    x = rng.standard_normal(n)
+    xd, yd = dev(x), torch.empty(m, dtype=torch.float64, device="cuda")
+    info = sb.operation_info_t()
+    sb.multiply_inspect(info, a, xd, yd)
+    sb.multiply_inspect(info, at, yd, xd)
+    calls = []
+    real = M._inspect
+    monkeypatch.setattr(M, "_inspect", lambda *args, **kw: (calls.append(1), real(*args, **kw))[1])
+    cp, ri = rp, ci                                  # transposed(a): the CSC of A^T over the same arrays
+    t_rp, t_ci, perm = oracle.csc_row_major_image((n, m), cp, ri)
+    for it in range(3):
+        sb.multiply_execute(info, a, xd, yd)
+        torch.cuda.synchronize()
+        assert info.spmv_variant in (0, 1, 2)
+        y_ref = oracle.spmv("csr", (m, n), rp, ci, v, x)
+        assert_rows_within_bound(yd.cpu().numpy(), y_ref, rp, oracle.abs_rowsum(rp, ci, v, x),
+                                 f"A x, iteration {it}")
+        y = yd.cpu().numpy()
+        sb.multiply_execute(info, at, yd, xd)
+        torch.cuda.synchronize()
+        x_ref = oracle.spmv("csc", (n, m), cp, ri, v, y)
+        assert_rows_within_bound(xd.cpu().numpy(), x_ref, t_rp,
+                                 oracle.abs_rowsum(t_rp, t_ci, v[perm], y), f"A^T y, iteration {it}")
+        x = xd.cpu().numpy()
+    assert not calls, "an execute re-inspected although both structures had been inspected"
+    info.close()

@@ -132,3 +132,39 @@ def test_hub_column_definition_known_answer(oracle):
     assert len(hubs) == 0 and refs == 0 and enc.tolist() == ci.tolist()
     hubs, refs, enc = oracle.hub_columns(np.array([], dtype=np.int32), 4, 8, 1)
     assert len(hubs) == 0 and refs == 0 and len(enc) == 0
+
+
+def test_one_info_keeps_a_plan_per_inspected_structure(monkeypatch):
+    """The reference's notes inspect `a` and `transposed(a)` with ONE operation_info_t and
+    alternate the executes (notes/spmv.hpp:12-22): the info keeps one plan per structure
+    (current + 3 parked, least recently used evicted) instead of re-inspecting at every
+    switch.  Pure host logic: plan handles are faked."""
+    import ctypes as C
+    import sys
+    M = sys.modules["spblas_reference_b200.multiply"]     # (the package exports the function)
+    destroyed = []
+    monkeypatch.setattr(M, "_destroy_plan", lambda plan: destroyed.append(plan.value))
+    info = M.operation_info_t()
+    assert not info._select("A")                      # nothing inspected yet
+
+    def inspect(sig, handle):                         # what every _inspect does
+        info._begin_inspect(sig)
+        if not info._plan:
+            info._plan = C.c_void_p(handle)           # (_ensure would create it)
+        info._sig = sig
+        return info._plan.value
+
+    assert inspect("A", 1) == 1
+    assert inspect("At", 2) == 2                      # A's plan is parked, not reused
+    assert info._select("A") and info._plan.value == 1 and info._sig == "A"
+    assert info._select("At") and info._plan.value == 2
+    assert info._select("A") and info._plan.value == 1 and not destroyed
+    assert inspect("A", 99) == 1                      # re-inspect: same plan, in place
+    assert inspect("B", 3) == 3 and inspect("C", 4) == 4
+    assert not destroyed                              # current C + parked At, A, B
+    assert inspect("D", 5) == 5                       # a fifth structure evicts the oldest
+    assert destroyed == [2] and not info._select("At")
+    assert info._select("A") and info._plan.value == 1
+    info.close()
+    assert sorted(destroyed) == [1, 2, 3, 4, 5]
+    assert not info._plan and info._parked == []
