@@ -1,0 +1,69 @@
+"""The C++ drop-in headers against every operand spelling user code uses (no GPU: g++
+-fsyntax-only of tests/cpp/compile_only.cpp with the reference's own headers).  A template that
+only binds lvalues compiles in the hand-written tests and breaks in a user's build — as
+multiply_inspect(info, transposed(a), ...) and multiply_inspect(matrix_opt(a), ...) did until
+the end of round 2.  Needs the reference tree (the headers are used where they lie): skipped on a
+box without /root/reference."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("SPBLAS_REFERENCE", "/root/reference")
+OVERLAY = os.path.join(ROOT, "build", "ref_overlay")
+CUDA_INC = "/usr/local/cuda/targets/x86_64-linux/include"
+
+
+def _syntax_check(source, extra=()):
+    cmd = ["g++", "-std=c++23", "-O0", "-w", "-fsyntax-only", "-DSPBLAS_ENABLE_B200",
+           f"-I{OVERLAY}/include", f"-I{ROOT}/include", f"-I{REF}/include",
+           f"-I{ROOT}/oracle/shim", f"-I{CUDA_INC}", *extra, source]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+
+
+@pytest.fixture(scope="module")
+def overlay():
+    if not os.path.isdir(os.path.join(REF, "include", "spblas")):
+        pytest.skip("reference tree not present")
+    if shutil.which("g++") is None or not os.path.isdir(CUDA_INC):
+        pytest.skip("g++ or the CUDA headers are missing")
+    # the five patched reference headers (integration/enable_b200.patch) as copies
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"),
+                        os.path.join(OVERLAY, ".stamp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return OVERLAY
+
+
+def test_every_overload_with_every_operand_spelling(overlay):
+    r = _syntax_check(os.path.join(ROOT, "tests", "cpp", "compile_only.cpp"))
+    assert r.returncode == 0, r.stderr[-4000:]
+
+
+def test_the_check_is_not_vacuous(overlay, tmp_path):
+    """-fsyntax-only must instantiate the templates: a call with a wrong operand has to fail."""
+    src = open(os.path.join(ROOT, "tests", "cpp", "compile_only.cpp")).read()
+    bad = src.replace("  multiply(a, x, y);\n", "  multiply(a, x, y);\n  multiply(a, 3, y);\n", 1)
+    assert bad != src
+    p = tmp_path / "compile_only_bad.cpp"
+    p.write_text(bad)
+    r = _syntax_check(str(p))
+    assert r.returncode != 0 and "error" in r.stderr
+
+
+def test_mixed_scalar_types_are_refused_at_compile_time(overlay, tmp_path):
+    """one scalar type for A, x and y (f32 / f64 / int32) — a mixed call
+    is a compile error that names the backend, not a silent conversion."""
+    p = tmp_path / "mixed.cpp"
+    p.write_text('''
+#include <span>
+#include <spblas/spblas.hpp>
+void f(float* v, int* rp, int* ci, double* x, double* y) {
+  spblas::csr_view<float, int, int> a(v, rp, ci, spblas::index<int>(4, 4), 4);
+  spblas::multiply(a, std::span<double>(x, 4), std::span<double>(y, 4));
+}
+int main() { return 0; }
+''')
+    r = _syntax_check(str(p))
+    assert r.returncode != 0
