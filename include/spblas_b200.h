@@ -215,7 +215,11 @@ SPBLAS_B200_API int spblas_b200_spmv_host(spblas_b200_plan* plan, int val_type,
                                           void* d_y);
 
 /* C[m x k] = alpha * A * B[n x k], B and C row-major with leading dimensions
-   ldb, ldc (>= k) in elements. */
+   ldb, ldc (>= k) in elements.  Two kernels (SPBLAS_B200_Q_SPMM_VARIANT: < 1000 one group of
+   lanes per row, >= 1000 merge-path warp streams): the streams when a row of B is at least
+   256 bytes, and at any width when the inspect phase's row-length histogram
+   (SPBLAS_B200_Q_ROWLEN_HIST) shows heavy-tailed rows — at least 10 % of the stored entries
+   in rows of 256 entries or more. */
 SPBLAS_B200_API int spblas_b200_spmm(spblas_b200_plan* plan, int val_type,
                                      const void* alpha, const void* d_values,
                                      const void* d_B, int64_t ldb, void* d_C,
