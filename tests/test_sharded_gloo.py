@@ -1,4 +1,4 @@
-"""Row-block sharding over torch.distributed with the gloo backend, world_size 2, on CPU:
+"""Row-block sharding over torch.distributed with the gloo backend, world_size 2, 3 and 4, on CPU:
 the partitioners, the halo / allgather exchange plan and the ping-pong y -> x step.  The
 local product is done by the ORACLE here (this is a test; the product path is GPU only)."""
 import os
@@ -99,9 +99,11 @@ def _worker(rank, world, port, kind, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 3, 4])
 @pytest.mark.parametrize("kind,mode", [("poisson", "halo"), ("rmat", "allgather")])
-def test_sharded_iteration_world2(kind, mode):
-    world = 2
+def test_sharded_iteration(kind, mode, world):
+    """world 3 and 4: a middle rank has TWO neighbours (the case that once scattered every tile
+    on the GPU path), and 576 rows do not split evenly into R-MAT's nnz-balanced blocks."""
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), kind, out), nprocs=world, join=True)
@@ -109,5 +111,5 @@ def test_sharded_iteration_world2(kind, mode):
     for rank in range(world):
         got_mode, ok, recv = out[rank]
         assert got_mode == mode and ok
-        if kind == "poisson":
-            assert recv == 24                                   # one grid line from the neighbour
+        if kind == "poisson":                                   # one grid line per neighbour
+            assert recv == (24 if rank in (0, world - 1) else 48)
