@@ -40,7 +40,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-ALIGN_STEPS = 8        # N > 1: untimed steps queued between the host barrier and the start event
+ALIGN_STEPS = 8        # untimed steps queued between the host barrier and the start event
 sys.path.insert(0, ROOT)
 
 
@@ -364,7 +364,9 @@ def main():
     # one-off that 20 steps of 0.23 ms would carry as "per step".  ALIGN untimed steps are
     # queued behind the barrier and ahead of the start event (no host synchronisation in
     # between): the in-kernel flag barrier brings the GPUs into lock-step before the clock starts.
-    align = ALIGN_STEPS if world > 1 else 0
+    # N = 1 runs them too: the GPU has just idled while the clock sampler started (up to a
+    # second), and the first steps after an idle period run below the clocks of the loop.
+    align = ALIGN_STEPS
     for _ in range(align):
         op.step()
     launches0 = info.total_launches
